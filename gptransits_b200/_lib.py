@@ -1,0 +1,93 @@
+"""ctypes binding of the C ABI in include/gptransits_b200.h.
+
+There is no CPU fallback: if the CUDA library is missing or cannot be loaded the
+import of the product path fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgptransits_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "kernels.cuh", "device_math.cuh")]
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "gptransits_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+
+class GptError(RuntimeError):
+    pass
+
+
+class Prior(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("ncomp", C.c_int32), ("comp_type", C.POINTER(C.c_int32)), ("has_transit", C.c_int32),
+                ("tr_fixed", C.c_double * 9), ("tr_free", C.c_uint8 * 9), ("supersample", C.c_int32),
+                ("exp_time_days", C.c_double), ("ellip_mode", C.c_int32), ("inc_mode", C.c_int32), ("ndim", C.c_int32),
+                ("priors", C.POINTER(Prior))]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree with nvcc for sm_100a."""
+    newest = max(os.path.getmtime(p) for p in SOURCES + [HEADER])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, SOURCES[0]]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in include/gptransits_b200.h
+SIGNATURES = {
+    "gpt_engine_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "gpt_engine_destroy": (None, [_vp]),
+    "gpt_last_error": (C.c_char_p, [_vp]),
+    "gpt_version": (C.c_char_p, []),
+    "gpt_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "gpt_get_stat": (C.c_int, [_vp, C.c_char_p, _dp]),
+    "gpt_model_set": (C.c_int, [_vp, C.POINTER(ModelDesc)]),
+    "gpt_star_upload": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int64]),
+    "gpt_star_clear": (C.c_int, [_vp]),
+    "gpt_log_prob": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp]),
+    "gpt_log_prob_multi": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
+    "gpt_log_prob_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "gpt_transit_flux": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp]),
+    "gpt_sample": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64,
+                             C.c_double, _dp, _dp, _i64p]),
+    "gpt_sampler_begin": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, _dp, C.c_int, C.c_uint64, C.c_uint64,
+                                    C.c_double]),
+    "gpt_sampler_run": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "gpt_sampler_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp, _dp]),
+    "gpt_sampler_state": (C.c_int, [_vp, _dp, _dp, _i64p]),
+    "gpt_sampler_end": (C.c_int, [_vp]),
+    "gpt_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+}
+
+
+def lib():
+    """Load libgptransits_b200.so (built by __graft_entry__.build()); raise if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GptError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib

@@ -1,0 +1,783 @@
+// engine.cu -- host side of the C ABI declared in include/gptransits_b200.h.
+// Owns device copies of the light curves, the workspaces of one evaluation batch, and the
+// device-resident sampler state.  No torch types, no CPU fallback: every result comes from the
+// kernels in kernels.cuh.
+#include "../../include/gptransits_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gpt;
+
+#define CK(call)                                                                                   \
+	do {                                                                                       \
+		cudaError_t _e = (call);                                                           \
+		if (_e != cudaSuccess) {                                                           \
+			e->set_error(std::string(#call) + ": " + cudaGetErrorString(_e));          \
+			return GPT_E_CUDA;                                                         \
+		}                                                                                  \
+	} while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8;
+		cudaError_t err = cudaMalloc((void **)&p, want * sizeof(T));
+		if (err == cudaSuccess) cap = want;
+		return err;
+	}
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct Star {
+	double4 *samp = nullptr;
+	int N = 0;
+	double dt0 = 0, dreg = 0, dmax = 0;
+	bool has_err = false;
+};
+
+}  // namespace
+
+struct gpt_engine {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	bool have_model = false;
+	ModelDev model;
+	bool may_generic = false;
+	std::vector<Star> stars;
+	DevBuf<StarDev> d_stars;
+	bool stars_dirty = true;
+
+	// options
+	int opt_halo = 0;        // 0 = auto
+	int opt_chunks = 0;      // 0 = auto
+	int opt_verify = 1;
+	int opt_halo_auto = 1;
+	double opt_tol = 1e-11;
+	int cur_halo = 192;
+
+	// stats
+	long long n_launch = 0, n_pass2_calls = 0, n_pass2_chunks = 0, n_evals = 0;
+	double last_verr = 0.0;
+	int last_chunks = 0, last_L = 0, last_H = 0;
+
+	// evaluation workspaces
+	DevBuf<double> d_theta, d_lp, d_parts, d_prep, d_mean, d_carryT, d_carryE;
+	DevBuf<int> d_flags, d_wstatus;
+	DevBuf<ChunkPartial> d_partial;
+	DevBuf<unsigned char> d_redo;
+	DevBuf<int> d_nbad;      // [1] + verr as 2 ints
+	DevBuf<double> d_verr;   // [1]
+	int *h_nbad = nullptr;   // pinned
+	double *h_verr = nullptr;
+
+	// sampler
+	bool sampling = false;
+	SamplerDev S;
+	int s_star0 = 0;
+	unsigned long long s_step = 0;
+	long long s_kept = 0;
+	DevBuf<double> s_x, s_lpx, s_q, s_lq, s_fac, s_chain, s_logp;
+	DevBuf<int> s_act, s_ids;
+	DevBuf<long long> s_nacc;
+
+	void set_error(const std::string &m) { err = m; }
+};
+
+// ---------------------------------------------------------------------------------------------
+static int sync_stars(gpt_engine *e)
+{
+	if (!e->stars_dirty) return GPT_OK;
+	std::vector<StarDev> h(e->stars.size());
+	for (size_t i = 0; i < h.size(); i++) {
+		h[i].samp = e->stars[i].samp;
+		h[i].N = e->stars[i].N;
+		h[i]._pad = 0;
+		h[i].dt0 = e->stars[i].dt0;
+		h[i].dreg = e->stars[i].dreg;
+		h[i].dmax = e->stars[i].dmax;
+	}
+	CK(e->d_stars.ensure(std::max<size_t>(1, h.size())));
+	if (!h.empty())
+		CK(cudaMemcpyAsync(e->d_stars.p, h.data(), h.size() * sizeof(StarDev), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->stars_dirty = false;
+	return GPT_OK;
+}
+
+static int check_stars(gpt_engine *e, int star0, int nstars)
+{
+	if (!e->have_model) {
+		e->set_error("no model: call gpt_model_set first");
+		return GPT_E_NOMODEL;
+	}
+	if (star0 < 0 || nstars < 1 || (size_t)(star0 + nstars) > e->stars.size()) {
+		e->set_error("star index out of range");
+		return GPT_E_NOSTAR;
+	}
+	int N = e->stars[star0].N;
+	for (int s = star0; s < star0 + nstars; s++) {
+		if (!e->stars[s].samp) {
+			e->set_error("star slot empty");
+			return GPT_E_NOSTAR;
+		}
+		if (e->stars[s].N != N) {
+			e->set_error("all stars of one batch must have the same number of samples");
+			return GPT_E_INVALID;
+		}
+	}
+	return GPT_OK;
+}
+
+// chunk geometry: enough (walker, chunk) threads to give every SM sub-partition ~2 warps
+static void pick_geometry(gpt_engine *e, int N, int W, int nstars, int &nchunks, int &L, int &H)
+{
+	H = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
+	int nc;
+	if (e->opt_chunks > 0) {
+		nc = e->opt_chunks;
+	} else {
+		long long warps_per_layer = (long long)nstars * ((W + 31) / 32);
+		long long target = 148LL * 8;
+		nc = (int)std::max<long long>(1, (target + warps_per_layer - 1) / warps_per_layer);
+		int maxc = std::max(1, N / std::max(2 * H, 64));
+		nc = std::min(nc, maxc);
+	}
+	nc = std::max(1, std::min(nc, N));
+	L = (N + nc - 1) / nc;
+	nchunks = (N + L - 1) / L;
+	if (nchunks == 1) H = 0;
+	H = std::min(H, L);
+}
+
+template <int NT>
+static void launch_chunk_nt(bool transit, dim3 grid, cudaStream_t st, const ChunkArgs &a)
+{
+	if (transit)
+		gp_chunk_kernel<NT, true><<<grid, CHUNK_THREADS, 0, st>>>(a);
+	else
+		gp_chunk_kernel<NT, false><<<grid, CHUNK_THREADS, 0, st>>>(a);
+}
+
+static void launch_chunk(int nt, bool transit, dim3 grid, cudaStream_t st, const ChunkArgs &a)
+{
+	switch (nt) {
+	case 1: launch_chunk_nt<1>(transit, grid, st, a); break;
+	case 2: launch_chunk_nt<2>(transit, grid, st, a); break;
+	case 3: launch_chunk_nt<3>(transit, grid, st, a); break;
+	case 4: launch_chunk_nt<4>(transit, grid, st, a); break;
+	default: break;
+	}
+}
+
+// Enqueue one posterior evaluation of nstars*W walkers.  theta/lp/parts are device pointers.
+// host_sync: read the verification verdict back and launch pass 2 only when needed; otherwise pass 2
+// is always enqueued (it exits immediately when nothing was flagged) so the sequence is graph-safe.
+static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
+			double *d_parts, bool host_sync)
+{
+	int rc = check_stars(e, star0, nstars);
+	if (rc) return rc;
+	rc = sync_stars(e);
+	if (rc) return rc;
+	const ModelDev &m = e->model;
+	const int N = e->stars[star0].N;
+	const int nwalk = nstars * W;
+	const int nt = m.nterms;
+	const StarDev *dst = e->d_stars.p + star0;
+	cudaStream_t st = e->stream;
+
+	CK(e->d_prep.ensure((size_t)nwalk * PREP_STRIDE));
+	CK(e->d_flags.ensure(nwalk));
+	CK(e->d_wstatus.ensure(nwalk));
+	CK(e->d_nbad.ensure(1));
+	CK(e->d_verr.ensure(1));
+	if (m.has_transit) CK(e->d_mean.ensure((size_t)nwalk * N));
+
+	CK(cudaMemsetAsync(e->d_wstatus.p, 0, sizeof(int) * nwalk, st));
+	CK(cudaMemsetAsync(e->d_nbad.p, 0, sizeof(int), st));
+	CK(cudaMemsetAsync(e->d_verr.p, 0, sizeof(double), st));
+	prep_kernel<<<(nwalk + 127) / 128, 128, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p);
+	e->n_launch++;
+	if (m.has_transit) {
+		dim3 g((N + TR_THREADS - 1) / TR_THREADS, nwalk);
+		transit_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode, e->d_prep.p,
+							 e->d_flags.p, e->d_mean.p, 0);
+		e->n_launch++;
+	}
+	e->n_evals += nwalk;
+
+	if (nt == 0) {
+		DiagArgs a;
+		a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
+		a.lp = d_lp; a.parts = d_parts; a.W = W; a.nwalk = nwalk; a.N = N;
+		a.gp = m.ncomp > 0; a.transit = m.has_transit; a.has_err = e->stars[star0].has_err;
+		diag_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(a);
+		e->n_launch++;
+		CK(cudaGetLastError());
+		return GPT_OK;
+	}
+
+	int nchunks, L, H;
+	pick_geometry(e, N, W, nstars, nchunks, L, H);
+	e->last_chunks = nchunks;
+	e->last_L = L;
+	e->last_H = H;
+	const int J = 2 * nt, CS = J * (J + 1) / 2 + J;
+	CK(e->d_carryT.ensure((size_t)nwalk * nchunks * CS));
+	CK(e->d_carryE.ensure((size_t)nwalk * nchunks * CS));
+	CK(e->d_partial.ensure((size_t)nwalk * nchunks));
+	CK(e->d_redo.ensure((size_t)nwalk * nchunks));
+
+	ChunkArgs a;
+	a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
+	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
+	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p;
+	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
+	dim3 grid(nchunks, (W + CHUNK_THREADS - 1) / CHUNK_THREADS, nstars);
+	launch_chunk(nt, m.has_transit != 0, grid, st, a);
+	e->n_launch++;
+
+	FinalArgs f;
+	f.prep = e->d_prep.p; f.flags = e->d_flags.p; f.wstatus = e->d_wstatus.p;
+	f.carryT = e->d_carryT.p; f.carryE = e->d_carryE.p; f.partial = e->d_partial.p; f.redo = e->d_redo.p;
+	f.nbad = e->d_nbad.p; f.lp = d_lp; f.parts = d_parts; f.verr = e->d_verr.p;
+	f.nwalk = nwalk; f.N = N; f.nchunks = nchunks; f.H = H; f.nterms = nt;
+	f.verify = (nchunks > 1 && e->opt_verify) ? 1 : 0;
+	f.tol = e->opt_tol;
+	gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+	e->n_launch++;
+
+	if (e->may_generic) {
+		GenericArgs g;
+		g.stars = dst; g.prep = e->d_prep.p; g.flags = e->d_flags.p; g.mean = e->d_mean.p;
+		g.lp = d_lp; g.parts = d_parts; g.W = W; g.nwalk = nwalk; g.N = N; g.nterms = nt;
+		g.transit = m.has_transit;
+		gp_generic_kernel<<<(nwalk + 31) / 32, 32, 0, st>>>(g);
+		e->n_launch++;
+	}
+
+	if (f.verify) {
+		bool need = true;
+		if (host_sync) {
+			CK(cudaMemcpyAsync(e->h_nbad, e->d_nbad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(e->h_verr, e->d_verr.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			need = *e->h_nbad > 0;
+			e->last_verr = *e->h_verr;
+			if (need) {
+				e->n_pass2_calls++;
+				e->n_pass2_chunks += *e->h_nbad;
+			}
+			if (e->opt_halo_auto && e->opt_halo == 0) {
+				// geometric decay model: ratio r at halo H, O(1e12) at H = 0
+				double r = need ? 1e3 : std::max(e->last_verr, 1e-30);
+				double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(1e-2);
+				double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
+				int nh = (int)std::ceil(want / 16.0) * 16;
+				nh = std::max(32, std::min(nh, 4096));
+				if (nh > e->cur_halo)
+					e->cur_halo = nh;
+				else
+					e->cur_halo = std::max(nh, (int)(e->cur_halo * 0.9));
+			}
+		}
+		if (need) {
+			a.pass2 = 1;
+			launch_chunk(nt, m.has_transit != 0, grid, st, a);
+			f.verify = 0;
+			gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+			e->n_launch += 2;
+		}
+	}
+	CK(cudaGetLastError());
+	return GPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *gpt_version(void) { return "gptransits_b200 0.1 (sm_100a)"; }
+
+int gpt_engine_create(int device, gpt_engine **out)
+{
+	if (!out) return GPT_E_INVALID;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return GPT_E_CUDA;
+	if (cudaSetDevice(device) != cudaSuccess) return GPT_E_CUDA;
+	gpt_engine *e = new gpt_engine();
+	e->device = device;
+	if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaMallocHost((void **)&e->h_nbad, sizeof(int)) != cudaSuccess ||
+	    cudaMallocHost((void **)&e->h_verr, sizeof(double)) != cudaSuccess) {
+		delete e;
+		return GPT_E_CUDA;
+	}
+	memset(&e->model, 0, sizeof(e->model));
+	memset(&e->S, 0, sizeof(e->S));
+	*out = e;
+	return GPT_OK;
+}
+
+int gpt_star_clear(gpt_engine *e)
+{
+	if (!e) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	for (auto &s : e->stars)
+		if (s.samp) cudaFree(s.samp);
+	e->stars.clear();
+	e->stars_dirty = true;
+	return GPT_OK;
+}
+
+void gpt_engine_destroy(gpt_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	gpt_star_clear(e);
+	e->d_stars.release();
+	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
+	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
+	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release();
+	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
+	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
+	if (e->h_nbad) cudaFreeHost(e->h_nbad);
+	if (e->h_verr) cudaFreeHost(e->h_verr);
+	cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+const char *gpt_last_error(const gpt_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int gpt_set_option(gpt_engine *e, const char *key, double value)
+{
+	if (!e || !key) return GPT_E_INVALID;
+	std::string k(key);
+	if (k == "halo") {
+		e->opt_halo = (int)value;
+	} else if (k == "chunks") {
+		e->opt_chunks = (int)value;
+	} else if (k == "verify") {
+		e->opt_verify = value != 0;
+	} else if (k == "halo_auto") {
+		e->opt_halo_auto = value != 0;
+	} else if (k == "verify_tol") {
+		e->opt_tol = value;
+	} else if (k == "halo_start") {
+		e->cur_halo = std::max(0, (int)value);
+	} else {
+		e->set_error("unknown option: " + k);
+		return GPT_E_INVALID;
+	}
+	return GPT_OK;
+}
+
+int gpt_get_stat(gpt_engine *e, const char *key, double *value)
+{
+	if (!e || !key || !value) return GPT_E_INVALID;
+	std::string k(key);
+	if (k == "launches") *value = (double)e->n_launch;
+	else if (k == "pass2_calls") *value = (double)e->n_pass2_calls;
+	else if (k == "pass2_chunks") *value = (double)e->n_pass2_chunks;
+	else if (k == "evals") *value = (double)e->n_evals;
+	else if (k == "verify_ratio") *value = e->last_verr;
+	else if (k == "chunks") *value = e->last_chunks;
+	else if (k == "chunk_len") *value = e->last_L;
+	else if (k == "halo") *value = e->last_H;
+	else if (k == "halo_next") *value = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
+	else if (k == "nstars") *value = (double)e->stars.size();
+	else {
+		e->set_error("unknown stat: " + k);
+		return GPT_E_INVALID;
+	}
+	return GPT_OK;
+}
+
+int gpt_model_set(gpt_engine *e, const gpt_model_desc *d)
+{
+	if (!e || !d) return GPT_E_INVALID;
+	if (d->ncomp < 0 || d->ncomp > MAX_COMP || d->ndim < 1 || d->ndim > MAX_NDIM) {
+		e->set_error("model: ncomp or ndim out of range");
+		return GPT_E_INVALID;
+	}
+	if (d->ncomp == 0 && !d->has_transit) {
+		e->set_error("model: need at least a gp or transit model");  // model.py:199-201
+		return GPT_E_INVALID;
+	}
+	ModelDev m;
+	memset(&m, 0, sizeof(m));
+	m.ncomp = d->ncomp;
+	int ndim_gp = 0, nterms = 0;
+	bool may_generic = false;
+	for (int c = 0; c < d->ncomp; c++) {
+		int t = d->comp_type[c];
+		if (t < 0 || t > 2) {
+			e->set_error("model: component type not recognized");  // gp.py:26-27
+			return GPT_E_INVALID;
+		}
+		m.comp_type[c] = t;
+		if (t == GPT_COMP_OSCILLATION_BUMP) {
+			// Q is the second parameter; Q < 1/2 turns the term into two real celerite terms
+			if (ndim_gp + 1 < d->ndim) {
+				const gpt_prior &pq = d->priors[ndim_gp + 1];
+				if (pq.kind == GPT_PRIOR_NORMAL || pq.a < 0.5) may_generic = true;
+			}
+		}
+		ndim_gp += t == 0 ? 2 : (t == 1 ? 3 : 1);
+		if (t != GPT_COMP_WHITE_NOISE) nterms++;
+	}
+	if (nterms > MAX_TERMS) {
+		e->set_error("model: more than 4 SHO terms are not supported");
+		return GPT_E_UNSUPPORTED;
+	}
+	int nfree = 0;
+	if (d->has_transit)
+		for (int i = 0; i < 9; i++) nfree += d->tr_free[i] ? 1 : 0;
+	if (ndim_gp + nfree != d->ndim) {
+		e->set_error("model: ndim does not match components + free transit parameters");
+		return GPT_E_INVALID;
+	}
+	m.nterms = nterms;
+	m.ndim = d->ndim;
+	m.ndim_gp = ndim_gp;
+	m.has_transit = d->has_transit ? 1 : 0;
+	m.supersample = d->supersample < 1 ? 1 : d->supersample;
+	m.exp_time = d->exp_time_days;
+	m.ellip_mode = d->ellip_mode;
+	m.inc_mode = d->inc_mode;
+	for (int i = 0; i < d->ndim; i++) {
+		if (d->priors[i].kind < 0 || d->priors[i].kind > 2) {
+			e->set_error("model: prior distribution not recognized");  // component.py:42-44
+			return GPT_E_INVALID;
+		}
+		m.prior_kind[i] = d->priors[i].kind;
+		m.prior_a[i] = d->priors[i].a;
+		m.prior_b[i] = d->priors[i].b;
+	}
+	for (int i = 0; i < 9; i++) {
+		m.tr_fixed[i] = d->tr_fixed[i];
+		m.tr_free[i] = d->tr_free[i];
+	}
+	e->model = m;
+	e->may_generic = may_generic;
+	e->have_model = true;
+	return GPT_OK;
+}
+
+int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double *y, const double *yerr, int64_t N)
+{
+	if (!e || !t_days || !y || N < 1 || N > (int64_t)1 << 30 || star < 0) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	if ((size_t)star >= e->stars.size()) e->stars.resize(star + 1);
+	Star &s = e->stars[star];
+	CK(cudaStreamSynchronize(e->stream));
+	if (s.samp) cudaFree(s.samp);
+	s.samp = nullptr;
+	std::vector<double4> h(N);
+	std::vector<double> dts;
+	dts.reserve(N);
+	double xprev = 0.0;
+	for (int64_t n = 0; n < N; n++) {
+		double x = t_days[n] * kDaysToMs;  // model.py:183-187
+		double dt = n ? x - xprev : 0.0;
+		xprev = x;
+		double err = yerr ? yerr[n] : 1.123e-12;  // celerite GP.compute default
+		h[n].x = dt;
+		h[n].y = y[n];
+		h[n].z = err * err;
+		h[n].w = t_days[n];
+		if (n) dts.push_back(dt);
+	}
+	double dt0 = 0.0;
+	if (!dts.empty()) {
+		std::vector<double> tmp(dts);
+		std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
+		dt0 = tmp[tmp.size() / 2];
+	}
+	double dreg = 1e-3 * std::fabs(dt0), dmax = 0.0;
+	for (double dt : dts)
+		if (std::fabs(dt - dt0) <= dreg) dmax = std::max(dmax, std::fabs(dt - dt0));
+	s.N = (int)N;
+	s.dt0 = dt0;
+	s.dreg = dreg;
+	s.dmax = dmax;
+	s.has_err = yerr != nullptr;
+	CK(cudaMalloc((void **)&s.samp, sizeof(double4) * N));
+	CK(cudaMemcpy(s.samp, h.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
+	e->stars_dirty = true;
+	return GPT_OK;
+}
+
+int gpt_log_prob_device(gpt_engine *e, int star0, int nstars, const double *theta_device, int W, double *lp_device,
+			double *parts_device)
+{
+	if (!e || !theta_device || !lp_device || W < 1) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	return eval_enqueue(e, star0, nstars, theta_device, W, lp_device, parts_device, false);
+}
+
+int gpt_log_prob_multi(gpt_engine *e, int star0, int nstars, const double *theta, int W, double *lp, double *parts)
+{
+	if (!e || !theta || !lp || W < 1 || nstars < 1) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	if (!e->have_model) {
+		e->set_error("no model: call gpt_model_set first");
+		return GPT_E_NOMODEL;
+	}
+	const size_t nwalk = (size_t)nstars * W;
+	const int ndim = e->model.ndim;
+	CK(e->d_theta.ensure(nwalk * ndim));
+	CK(e->d_lp.ensure(nwalk));
+	CK(e->d_parts.ensure(nwalk * 4));
+	CK(cudaMemcpyAsync(e->d_theta.p, theta, sizeof(double) * nwalk * ndim, cudaMemcpyHostToDevice, e->stream));
+	int rc = eval_enqueue(e, star0, nstars, e->d_theta.p, W, e->d_lp.p, parts ? e->d_parts.p : nullptr, true);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(lp, e->d_lp.p, sizeof(double) * nwalk, cudaMemcpyDeviceToHost, e->stream));
+	if (parts)
+		CK(cudaMemcpyAsync(parts, e->d_parts.p, sizeof(double) * nwalk * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return GPT_OK;
+}
+
+int gpt_log_prob(gpt_engine *e, int star, const double *theta, int W, double *lp, double *parts)
+{
+	return gpt_log_prob_multi(e, star, 1, theta, W, lp, parts);
+}
+
+int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double *flux)
+{
+	if (!e || !pars9 || !flux || W < 1) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	if (star < 0 || (size_t)star >= e->stars.size() || !e->stars[star].samp) {
+		e->set_error("star slot empty");
+		return GPT_E_NOSTAR;
+	}
+	if (!e->have_model) {
+		e->set_error("no model: call gpt_model_set first");
+		return GPT_E_NOMODEL;
+	}
+	int rc = sync_stars(e);
+	if (rc) return rc;
+	const int N = e->stars[star].N;
+	CK(e->d_theta.ensure((size_t)W * 9));
+	CK(e->d_prep.ensure((size_t)W * PREP_STRIDE));
+	CK(e->d_flags.ensure(W));
+	CK(e->d_mean.ensure((size_t)W * N));
+	CK(cudaMemcpyAsync(e->d_theta.p, pars9, sizeof(double) * W * 9, cudaMemcpyHostToDevice, e->stream));
+	prep_transit_direct_kernel<<<(W + 127) / 128, 128, 0, e->stream>>>(e->model.exp_time, e->d_theta.p, W, e->d_prep.p,
+									    e->d_flags.p);
+	dim3 g((N + TR_THREADS - 1) / TR_THREADS, W);
+	transit_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample, e->model.exp_time,
+							e->model.ellip_mode, e->d_prep.p, e->d_flags.p, e->d_mean.p, 1);
+	e->n_launch += 2;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(flux, e->d_mean.p, sizeof(double) * (size_t)W * N, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return GPT_OK;
+}
+
+// ------------------------------------------------------------------------------------- sampler
+int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_ids, const double *init, int W,
+		      uint64_t seed, uint64_t step0, double a)
+{
+	if (!e || !init || W < 2 || (W & 1) || nstars < 1) {
+		if (e) e->set_error("sampler: W must be even and >= 2");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	int rc = check_stars(e, star0, nstars);
+	if (rc) return rc;
+	const int ndim = e->model.ndim;
+	// emcee refuses W < 2*ndim unless live_dangerously; keep the same guard
+	if (W < 2 * ndim) {
+		e->set_error("sampler: need at least 2*ndim walkers (emcee RedBlueMove)");
+		return GPT_E_INVALID;
+	}
+	const size_t nw = (size_t)nstars * W, nh = (size_t)nstars * (W / 2);
+	CK(e->s_x.ensure(nw * ndim));
+	CK(e->s_lpx.ensure(nw));
+	CK(e->s_q.ensure(nh * ndim));
+	CK(e->s_lq.ensure(nh));
+	CK(e->s_fac.ensure(nh));
+	CK(e->s_act.ensure(nw));
+	CK(e->s_ids.ensure(nstars));
+	CK(e->s_nacc.ensure(nw));
+	std::vector<int> ids(nstars);
+	for (int i = 0; i < nstars; i++) ids[i] = star_ids ? star_ids[i] : star0 + i;
+	CK(cudaMemcpyAsync(e->s_ids.p, ids.data(), sizeof(int) * nstars, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->s_x.p, init, sizeof(double) * nw * ndim, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemsetAsync(e->s_nacc.p, 0, sizeof(long long) * nw, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	SamplerDev &S = e->S;
+	S.x = e->s_x.p; S.lpx = e->s_lpx.p; S.q = e->s_q.p; S.lq = e->s_lq.p; S.fac = e->s_fac.p;
+	S.act = e->s_act.p; S.nacc = e->s_nacc.p; S.star_ids = e->s_ids.p;
+	S.chain = nullptr; S.logp = nullptr; S.cap = 0;
+	S.W = W; S.ndim = ndim; S.nstars = nstars; S.seed = seed; S.a = a;
+	e->s_star0 = star0;
+	e->s_step = step0;
+	e->s_kept = 0;
+	// initial log-probabilities of the whole ensemble
+	rc = eval_enqueue(e, star0, nstars, S.x, W, S.lpx, nullptr, true);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(e->stream));
+	e->sampling = true;
+	return GPT_OK;
+}
+
+int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep)
+{
+	if (!e || nsteps < 0) return GPT_E_INVALID;
+	if (!e->sampling) {
+		e->set_error("sampler: gpt_sampler_begin not called");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	SamplerDev &S = e->S;
+	const int W = S.W, H = W / 2, ndim = S.ndim, ns = S.nstars;
+	if (keep) {
+		size_t nw = (size_t)ns * W;
+		CK(e->s_chain.ensure(nw * nsteps * ndim));
+		CK(e->s_logp.ensure(nw * nsteps));
+		S.chain = e->s_chain.p;
+		S.logp = e->s_logp.p;
+		S.cap = nsteps;
+		e->s_kept = 0;
+	}
+	cudaStream_t st = e->stream;
+	const int nh = ns * H;
+	for (int64_t s = 0; s < nsteps; s++) {
+		sampler_split_kernel<<<ns, 256, (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st>>>(S, e->s_step);
+		e->n_launch++;
+		for (int half = 0; half < 2; half++) {
+			sampler_propose_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
+			e->n_launch++;
+			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, true);
+			if (rc) return rc;
+			sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
+			e->n_launch++;
+		}
+		if (keep) {
+			sampler_record_kernel<<<(ns * W + 127) / 128, 128, 0, st>>>(S, e->s_kept);
+			e->n_launch++;
+			e->s_kept++;
+		}
+		e->s_step++;
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
+	return GPT_OK;
+}
+
+int gpt_sampler_read(gpt_engine *e, int64_t first, int64_t count, double *chain, double *logp)
+{
+	if (!e || !e->sampling || first < 0 || count < 0 || first + count > e->s_kept) {
+		if (e) e->set_error("sampler_read: range outside the kept steps");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	const SamplerDev &S = e->S;
+	const size_t W = S.W, ndim = S.ndim, ns = S.nstars, cap = S.cap;
+	// chain [ns][W][count][ndim] <- device [ns][W][cap][ndim]
+	if (chain)
+		CK(cudaMemcpy2DAsync(chain, count * ndim * sizeof(double), S.chain + first * ndim, cap * ndim * sizeof(double),
+				     count * ndim * sizeof(double), ns * W, cudaMemcpyDeviceToHost, e->stream));
+	if (logp)
+		CK(cudaMemcpy2DAsync(logp, count * W * sizeof(double), S.logp + first * W, cap * W * sizeof(double),
+				     count * W * sizeof(double), ns, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return GPT_OK;
+}
+
+int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *naccept)
+{
+	if (!e || !e->sampling) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	const SamplerDev &S = e->S;
+	const size_t nw = (size_t)S.nstars * S.W;
+	if (coords) CK(cudaMemcpyAsync(coords, S.x, sizeof(double) * nw * S.ndim, cudaMemcpyDeviceToHost, e->stream));
+	if (logp) CK(cudaMemcpyAsync(logp, S.lpx, sizeof(double) * nw, cudaMemcpyDeviceToHost, e->stream));
+	if (naccept) {
+		static_assert(sizeof(long long) == sizeof(int64_t), "");
+		CK(cudaMemcpyAsync(naccept, S.nacc, sizeof(int64_t) * nw, cudaMemcpyDeviceToHost, e->stream));
+	}
+	CK(cudaStreamSynchronize(e->stream));
+	return GPT_OK;
+}
+
+int gpt_sampler_end(gpt_engine *e)
+{
+	if (!e) return GPT_E_INVALID;
+	e->sampling = false;
+	return GPT_OK;
+}
+
+int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, int64_t nsteps, uint64_t seed,
+	       uint64_t step0, double a, double *chain, double *logp, int64_t *naccept)
+{
+	if (!e || !chain || !logp) return GPT_E_INVALID;
+	int rc = gpt_sampler_begin(e, star0, nstars, nullptr, init, W, seed, step0, a);
+	if (rc) return rc;
+	rc = gpt_sampler_run(e, nsteps, 1);
+	if (rc) return rc;
+	rc = gpt_sampler_read(e, 0, nsteps, chain, logp);
+	if (rc) return rc;
+	if (naccept) {
+		rc = gpt_sampler_state(e, nullptr, nullptr, naccept);
+		if (rc) return rc;
+	}
+	return gpt_sampler_end(e);
+}
+
+int gpt_measure_fp64_peak(gpt_engine *e, double *tflops)
+{
+	if (!e || !tflops) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+	DevBuf<double> out;
+	CK(out.ensure((size_t)blocks * threads));
+	cudaEvent_t a, b;
+	CK(cudaEventCreate(&a));
+	CK(cudaEventCreate(&b));
+	double best = 0.0;
+	for (int rep = 0; rep < 5; rep++) {
+		CK(cudaEventRecord(a, e->stream));
+		dfma_peak_kernel<<<blocks, threads, 0, e->stream>>>(out.p, iters);
+		CK(cudaEventRecord(b, e->stream));
+		CK(cudaEventSynchronize(b));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, a, b));
+		double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+		if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+	}
+	e->n_launch += 5;
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	out.release();
+	*tflops = best;
+	return GPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+/*
+ * gptransits_b200.h -- C ABI of the B200-native likelihood + sampling engine.
+ *
+ * The reference (Fill4/gptransits) has no FFI: its seams are Python call sites.
+ * Each entry point below names the reference interface it replaces
+ * (file:line into the reference tree).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative GPT_E_* code; nothing throws
+ *     across the ABI; gpt_last_error() gives the message for the last failure.
+ *   - all pointers are HOST memory owned by the caller unless the name ends in
+ *     _device; the engine owns its device copies.  Calls are synchronous.
+ *   - a per-walker numerical failure (prior out of support, non positive
+ *     definite covariance, NaN) is NOT an error return: that walker's
+ *     log-probability is -inf, exactly as model.py:302-303 and celerite's
+ *     log_likelihood do.
+ *   - all floating point is IEEE double.  theta is the flat walker vector
+ *     [GP component parameters in config order ..., free transit parameters in
+ *     (P,t0,Rrat,aR,cosi,e,w,u1,u2) order] (model.py:262,300-301,306,309).
+ *   - one engine = one GPU + one model structure + any number of stars.
+ *     One host thread per engine at a time.
+ */
+#ifndef GPTRANSITS_B200_H
+#define GPTRANSITS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpt_engine gpt_engine;
+
+enum {
+	GPT_OK = 0,
+	GPT_E_INVALID = -1,   /* bad argument */
+	GPT_E_CUDA = -2,      /* CUDA runtime failure (message has the cudaError) */
+	GPT_E_NOMODEL = -3,   /* gpt_model_set not called */
+	GPT_E_NOSTAR = -4,    /* star slot empty */
+	GPT_E_UNSUPPORTED = -5
+};
+
+/* component.py:66,111,150 -- the three celerite term classes */
+enum { GPT_COMP_GRANULATION = 0, GPT_COMP_OSCILLATION_BUMP = 1, GPT_COMP_WHITE_NOISE = 2 };
+/* component.py:33-41, transit.py:56-64 -- scipy.stats frozen priors */
+enum { GPT_PRIOR_UNIFORM = 0, GPT_PRIOR_NORMAL = 1, GPT_PRIOR_RECIPROCAL = 2 };
+/* K and E of the Mandel-Agol flux: batman's Hastings polynomials (parity with
+ * the reference) or iterated to machine precision */
+enum { GPT_ELLIP_BATMAN = 0, GPT_ELLIP_EXACT = 1 };
+/* How the 5th transit parameter reaches batman's `inc` (degrees).  The reference assigns the
+ * value named `cosi` verbatim (transit.py:103); GPT_INC_FROM_COSI is the opt-in
+ * inc = degrees(arccos(cosi)). */
+enum { GPT_INC_VERBATIM = 0, GPT_INC_FROM_COSI = 1 };
+
+/* (kind, a, b) of one free parameter: uniform(a, b-a) | norm(a, b) | reciprocal(a, b) */
+typedef struct {
+	int32_t kind;
+	int32_t _pad;
+	double a, b;
+} gpt_prior;
+
+/* The model structure: what GPModel.__init__ (gp.py:10-29) and
+ * BatmanModel.__init__/init_model (transit.py:14-91) hold after construction. */
+typedef struct {
+	int32_t ncomp;              /* number of GP components (0 = transit only) */
+	const int32_t *comp_type;   /* [ncomp] GPT_COMP_* in config order */
+	int32_t has_transit;        /* 0 = GP only (model.py:315-325) */
+	double tr_fixed[9];         /* values of fixed transit parameters (transit.py:52-55) */
+	uint8_t tr_free[9];         /* BatmanModel.mask (transit.py:19,54) */
+	int32_t supersample;        /* batman supersample_factor (model.py:174: 6) */
+	double exp_time_days;       /* batman exp_time (transit.py:90) */
+	int32_t ellip_mode;         /* GPT_ELLIP_* */
+	int32_t inc_mode;           /* GPT_INC_* */
+	int32_t ndim;               /* number of free parameters = len(priors) */
+	const gpt_prior *priors;    /* [ndim] in theta order */
+} gpt_model_desc;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int gpt_engine_create(int device, gpt_engine **out);
+void gpt_engine_destroy(gpt_engine *e);
+const char *gpt_last_error(const gpt_engine *e);
+const char *gpt_version(void);
+
+/* Tunables ("halo", "chunks", "verify", "tile", ...) and counters
+ * ("launches", "pass2_chunks", "halo", "chunks", "last_kernel_ms", ...). */
+int gpt_set_option(gpt_engine *e, const char *key, double value);
+int gpt_get_stat(gpt_engine *e, const char *key, double *value);
+
+/* ---- model + data ------------------------------------------------------- */
+/* Replaces Model.setup_models (model.py:168-201): GPModel(config['gp']),
+ * BatmanModel(config['transit'][0]).init_model(time, cadence, 6). */
+int gpt_model_set(gpt_engine *e, const gpt_model_desc *desc);
+
+/* Replaces celerite.GP.compute(t*0.0864, yerr=...) (model.py:183-187) plus the
+ * light-curve members read by the likelihood (model.py:309-310: lc.time,
+ * lc.flux).  t in days, y and yerr in the flux unit the caller fits in (the
+ * reference: ppm).  yerr == NULL -> celerite's default 1.123e-12. */
+int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double *y,
+		    const double *yerr, int64_t N);
+int gpt_star_clear(gpt_engine *e);
+
+/* ---- posterior seam ----------------------------------------------------- */
+/* Replaces Model.full_lnlike / gp_lnlike / transit_lnlike (model.py:299-343)
+ * evaluated for W walkers at once: theta[W*ndim] row-major -> lp[W].
+ * parts (optional, [W*4]) = lnprior, quad (r^T K^-1 r), logdet, lnL. */
+int gpt_log_prob(gpt_engine *e, int star, const double *theta, int W, double *lp, double *parts);
+
+/* Same for nstars consecutive stars (all of length N): theta[nstars*W*ndim]. */
+int gpt_log_prob_multi(gpt_engine *e, int star0, int nstars, const double *theta, int W, double *lp,
+		       double *parts);
+
+/* Same with device pointers; asynchronous on the engine's stream. */
+int gpt_log_prob_device(gpt_engine *e, int star0, int nstars, const double *theta_device, int W,
+			double *lp_device, double *parts_device);
+
+/* Replaces BatmanModel.compute's batman call (transit.py:124-127 ->
+ * batman.TransitModel.light_curve): pars9[W*9] = per,t0,rp,a,inc[deg],ecc,w[deg],u1,u2
+ * in batman's own semantics; flux[W*N] = supersampled, exposure-averaged
+ * relative flux (1.0 out of transit). */
+int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double *flux);
+
+/* ---- sampler seam ------------------------------------------------------- */
+/* Replaces emcee.EnsembleSampler(W, ndim, lnlike).run_mcmc(init, nsteps)
+ * (model.py:270-284) with the default StretchMove(a) for nstars independent
+ * stars, each with its own ensemble:
+ *   init  [nstars][W][ndim]
+ *   chain [nstars][W][nsteps][ndim]   (sampler.chain, model.py:283)
+ *   logp  [nstars][nsteps][W]         (sampler.get_log_prob(), model.py:284)
+ *   naccept [nstars][W] (optional)
+ * step0 is the number of iterations already done (resume, model.py:235-253):
+ * the Philox stream is keyed by (seed, star id, step0 + i, walker) so results
+ * do not depend on how the run is split or on the number of GPUs.
+ * thin >= 1 keeps every thin-th step (nsteps must be a multiple). */
+int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, int64_t nsteps,
+	       uint64_t seed, uint64_t step0, double a, double *chain, double *logp, int64_t *naccept);
+
+/* Device-resident sampler, for callers that keep the chain on the GPU or shard
+ * an ensemble across GPUs.  star_ids (optional, [nstars]) are the GLOBAL star
+ * ids used in the RNG key (default star0 + i). */
+int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_ids, const double *init,
+		      int W, uint64_t seed, uint64_t step0, double a);
+/* advance nsteps; positions/log-probs stay on the device.  keep != 0 appends
+ * every step to the device chain buffer (read with gpt_sampler_read). */
+int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep);
+int gpt_sampler_read(gpt_engine *e, int64_t first, int64_t count, double *chain, double *logp);
+int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *naccept);
+int gpt_sampler_end(gpt_engine *e);
+
+/* FP64 FMA throughput of this GPU (TFLOP/s, FMA = 2), measured by a register
+ * resident DFMA kernel -- the roofline denominator bench.py reports against. */
+int gpt_measure_fp64_peak(gpt_engine *e, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -154,7 +154,7 @@ def _spec_args(spec):
     args = [C.c_int(ct.size), _ip(ct), C.c_int(int(spec.get("has_transit", 0))), _dp(fixed),
             free.ctypes.data_as(c_ubyte_p), C.c_int(kind.size), _ip(kind), _dp(pa), _dp(pb),
             C.c_int(int(spec.get("supersample", 1))), C.c_double(float(spec.get("exp_time", 0.0))),
-            C.c_int(int(spec.get("ellip_mode", 0)))]
+            C.c_int(int(spec.get("ellip_mode", 0))), C.c_int(int(spec.get("inc_mode", 0)))]
     return args, keep, kind.size
 
 

@@ -654,6 +654,7 @@ typedef struct {
 	int supersample;
 	double exp_time;
 	int ellip_mode;
+	int inc_mode; /* 0: transit.py:103 verbatim; 1: inc = degrees(arccos(cosi)) */
 	int N;
 	const double *t_days, *y, *yerr; /* yerr already the value celerite gets */
 } orc_model;
@@ -686,6 +687,7 @@ static double log_prob_one(const orc_model *m, const double *theta, double *part
 		int k = m->ndim_gp;
 		for (int i = 0; i < 9; i++) pars[i] = m->tr_free[i] ? theta[k++] : m->tr_fixed[i];
 		/* transit.py:99-106: per,t0,rp,a,inc,ecc,w,u1,u2 <- pars[0..8] verbatim */
+		if (m->inc_mode == 1) pars[4] = acos(pars[4]) * (180. / M_PI);
 		orc_light_curve(m->t_days, m->N, pars, m->supersample, m->exp_time, m->ellip_mode, flux);
 		for (int n = 0; n < m->N; n++) resid[n] = m->y[n] - (flux[n] - 1) * 1e6;
 		r = resid;
@@ -725,7 +727,7 @@ done:
 
 int orc_log_prob(int ncomp, const int *comp_type, int has_transit, const double *tr_fixed,
 		 const unsigned char *tr_free, int ndim, const int *prior_kind, const double *prior_a,
-		 const double *prior_b, int supersample, double exp_time, int ellip_mode, int N,
+		 const double *prior_b, int supersample, double exp_time, int ellip_mode, int inc_mode, int N,
 		 const double *t_days, const double *y, const double *yerr, const double *theta, int W,
 		 double *lp, double *parts, int nthreads)
 {
@@ -743,6 +745,7 @@ int orc_log_prob(int ncomp, const int *comp_type, int has_transit, const double 
 	m.supersample = supersample;
 	m.exp_time = exp_time;
 	m.ellip_mode = ellip_mode;
+	m.inc_mode = inc_mode;
 	m.N = N;
 	m.t_days = t_days;
 	m.y = y;
@@ -828,7 +831,7 @@ static double u53(uint32_t lo, uint32_t hi)
 /* ------------------------------------------------------------------------- */
 int orc_sample(int ncomp, const int *comp_type, int has_transit, const double *tr_fixed,
 	       const unsigned char *tr_free, int ndim, const int *prior_kind, const double *prior_a,
-	       const double *prior_b, int supersample, double exp_time, int ellip_mode, int N,
+	       const double *prior_b, int supersample, double exp_time, int ellip_mode, int inc_mode, int N,
 	       const double *t_days, const double *y, const double *yerr, int W, const double *init,
 	       long nsteps, uint64_t seed, uint32_t star, uint64_t step0, double a_stretch, double *chain,
 	       double *logp, long *naccept, int nthreads)
@@ -845,7 +848,7 @@ int orc_sample(int ncomp, const int *comp_type, int has_transit, const double *t
 	int *act = malloc(sizeof(int) * (size_t)H), *oth = malloc(sizeof(int) * (size_t)H);
 	memcpy(x, init, sizeof(double) * (size_t)W * ndim);
 	orc_log_prob(ncomp, comp_type, has_transit, tr_fixed, tr_free, ndim, prior_kind, prior_a, prior_b,
-		     supersample, exp_time, ellip_mode, N, t_days, y, yerr, x, W, lp, NULL, nthreads);
+		     supersample, exp_time, ellip_mode, inc_mode, N, t_days, y, yerr, x, W, lp, NULL, nthreads);
 	for (int w = 0; w < W; w++)
 		if (naccept) naccept[w] = 0;
 	for (long s = 0; s < nsteps; s++) {
@@ -885,7 +888,7 @@ int orc_sample(int ncomp, const int *comp_type, int has_transit, const double *t
 				}
 			}
 			orc_log_prob(ncomp, comp_type, has_transit, tr_fixed, tr_free, ndim, prior_kind, prior_a,
-				     prior_b, supersample, exp_time, ellip_mode, N, t_days, y, yerr, q, H, lq, NULL,
+				     prior_b, supersample, exp_time, ellip_mode, inc_mode, N, t_days, y, yerr, q, H, lq, NULL,
 				     nthreads);
 			for (int i = 0; i < H; i++) {
 				int w = act[i];

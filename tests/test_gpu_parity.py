@@ -1,0 +1,355 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerance: 1e-9 relative on quad, logdet, lnL and on the transit flux (BASELINE.json north_star),
+checked SEPARATELY for quad and logdet (with the 1e6 ppm baseline the total
+lnL would hide a log-det error).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from gptransits_b200 import BatmanModel, GPModel, build_spec
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def assert_parts_close(got, want, rtol=RTOL):
+    # columns: lnprior, quad, logdet, lnL
+    for col, name in enumerate(("lnprior", "quad", "logdet", "lnL")):
+        g, w = got[..., col], want[..., col]
+        fin = np.isfinite(w)
+        assert np.array_equal(np.isfinite(g), fin), name
+        if fin.any():
+            assert rel(g[fin], w[fin]) < rtol, (name, rel(g[fin], w[fin]))
+
+
+def kic_setup(kic_lc, kic_config, baseline_removed=False):
+    t, f, e = kic_lc
+    y = (f - 1) * 1e6 if baseline_removed else f * 1e6
+    gp = GPModel(kic_config["gp"])
+    return t, y, e * 1e6, build_spec(gp, None), gp
+
+
+@pytest.mark.parametrize("baseline_removed", [False, True])
+def test_kic_gp_only(engine, kic_lc, kic_config, golden, baseline_removed):
+    t, y, yerr, spec, gp = kic_setup(kic_lc, kic_config, baseline_removed)
+    theta = np.array(golden["kic-012008916"]["theta_gp"])
+    theta = np.vstack([theta, golden["kic-012008916"]["theta_gp_outside"]])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want_parts = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+    for chunks in (1, 2, 5, 0):
+        engine.set_option("chunks", chunks)
+        lp, parts = engine.log_prob(theta, return_parts=True)
+        assert_parts_close(parts, want_parts)
+        assert lp[-1] == -np.inf and want_lp[-1] == -np.inf
+        assert rel(lp[:-1], want_lp[:-1]) < RTOL
+    engine.set_option("chunks", 0)
+
+
+def test_kic_survey_golden_theta(engine, kic_lc, kic_config):
+    """theta_gp row, logdet = 14345.578386664782, quad = 981.5028166301665."""
+    t, y, yerr, spec, gp = kic_setup(kic_lc, kic_config, baseline_removed=True)
+    theta = np.array([[249.74246655, 5.19060939, 105.80836122, 368.63266001, 68.27098486, 88.68944315]])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    _, parts = engine.log_prob(theta, return_parts=True)
+    assert abs(parts[0, 2] / 14345.578386664782 - 1) < RTOL
+    assert abs(parts[0, 1] / 981.5028166301665 - 1) < RTOL
+    assert abs(parts[0, 3] / -8850.809186547911 - 1) < RTOL
+
+
+def sim_setup(sim_lc, sim_config, inc_mapping="reference"):
+    t, f, e = sim_lc
+    np.random.seed(42)
+    gp = GPModel(sim_config["gp"])
+    tr = BatmanModel(sim_config["transit"][0])
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr, {"inc_mapping": inc_mapping})
+    return t, f * 1e6, None, spec, gp, tr
+
+
+@pytest.mark.parametrize("inc_mapping", ["reference", "cosi"])
+def test_sim_gp_plus_transit(engine, sim_lc, sim_config, golden, inc_mapping):
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config, inc_mapping)
+    g = golden["sim-2452144"]
+    theta = np.hstack([np.array(g["theta_gp"]), np.array(g["theta_tr"])])
+    # realistic transiting geometry for the cosi mapping: b = aR*cosi < 1
+    extra = theta[:4].copy()
+    extra[:, 6:] = [[5.9, 3.0, 0.03, 10.0, 0.02], [5.8, 3.1, 0.08, 8.0, 0.11], [6.0, 2.9, 0.05, 12.0, 0.08],
+                    [5.9, 3.0, 0.099, 3.0, 0.3]]
+    theta = np.vstack([theta, extra])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want_parts = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+    for chunks in (1, 3, 0):
+        engine.set_option("chunks", chunks)
+        lp, parts = engine.log_prob(theta, return_parts=True)
+        assert_parts_close(parts, want_parts)
+    engine.set_option("chunks", 0)
+
+
+def test_transit_flux_matches_batman_restatement(engine, sim_lc, sim_config):
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    rng = np.random.default_rng(7)
+    pars = []
+    for _ in range(24):
+        pars.append([rng.uniform(2, 8), rng.uniform(2.8, 3.3), 10 ** rng.uniform(-2.5, -0.5), rng.uniform(3, 15),
+                     rng.uniform(84, 90), 0.0, 90.0, 0.4996, 0.0847])
+    # eccentric orbits, grazing and large planets, inclination past 90, negative rp, face-on
+    pars += [[5.9, 3.0, 0.1, 9.0, 87.0, 0.3, 40.0, 0.3, 0.2], [3.3, 3.1, 0.05, 6.0, 89.0, 0.6, 200.0, 0.5, 0.1],
+             [5.9, 3.0, 0.3, 4.0, 78.0, 0.0, 90.0, 0.4, 0.1], [5.9, 3.0, 1.2, 3.0, 85.0, 0.0, 90.0, 0.4, 0.1],
+             [5.9, 3.0, 0.05, 10.0, 93.0, 0.0, 90.0, 0.4, 0.1], [5.9, 3.0, -0.05, 10.0, 88.0, 0.0, 90.0, 0.4, 0.1],
+             [5.9, 3.0, 0.05, 1.02, 0.5, 0.0, 90.0, 0.4996, 0.0847], [5.9, 3.0, 0.05, 10.0, 88.0, 0.0, 90.0, 0.0, 0.0],
+             [0.7, 3.0, 0.1, 2.0, 80.0, 0.1, 10.0, 0.6, 0.0]]
+    pars = np.array(pars)
+    for mode in (0, 1):
+        spec_m = dict(spec, ellip_mode=mode)
+        engine.set_model(spec_m)
+        got = engine.transit_flux(pars)
+        for k, p in enumerate(pars):
+            want = oracle.light_curve(t, p, supersample=6, exp_time=spec["exp_time"], mode=mode)
+            assert np.array_equal(np.isnan(got[k]), np.isnan(want)), k
+            ok = ~np.isnan(want)
+            assert np.max(np.abs(got[k][ok] - want[ok])) < 1e-9 * 1.0, (mode, k, np.max(np.abs(got[k][ok] - want[ok])))
+        assert np.any(got < 1.0)
+    engine.set_model(spec)
+
+
+def synthetic_star(N, seed, cadence_min=29.4244, gap_every=4400):
+    rng = np.random.default_rng(seed)
+    t = np.arange(N) * (cadence_min / 1440.0) + (np.arange(N) // gap_every) * 1.0
+    y = 1e6 + 300 * np.sin(t * 3.1) + rng.normal(0, 120, N)
+    yerr = np.full(N, 50.0) * rng.uniform(0.9, 1.1, N)
+    return t, y, yerr
+
+
+C3_CONFIG_GP = [
+    {"type": "granulation", "params": {"values": {"a_gran": [False, None, "uniform", 150, 450],
+                                                  "b_gran": [False, None, "uniform", 25, 75]}}},
+    {"type": "granulation", "params": {"values": {"a_gran": [False, None, "uniform", 75, 225],
+                                                  "b_gran": [False, None, "uniform", 7.5, 22.5]}}},
+    {"type": "oscillation_bump", "params": {"values": {"P_g": [False, None, "uniform", 125, 375],
+                                                       "Q": [False, None, "uniform", 2.5, 7.5],
+                                                       "nu_max": [False, None, "uniform", 75, 225]}}},
+    {"type": "white_noise", "params": {"values": {"jitter": [False, None, "uniform", 50, 150]}}},
+]
+C3_CONFIG_TR = {"params": {"values": {
+    "P": [False, None, "uniform", 2.95, 8.85], "t0": [False, None, "uniform", 1.5, 4.5],
+    "Rrat": [False, None, "uniform", 0.015, 0.045], "aR": [False, None, "uniform", 5.0, 15.0],
+    "cosi": [False, None, "uniform", 86.0, 90.0],   # reference mapping: the value IS batman's inc in degrees
+    "e": [True, 0.0, "uniform", 0, 1], "w": [True, 90.0, "uniform", 0, 90],
+    "u1": [True, 0.4996, "uniform", 0, 1], "u2": [True, 0.0847, "uniform", 0, 1]}}}
+
+
+@pytest.mark.parametrize("N,irregular", [(8192, False), (8192, True), (20000, False)])
+def test_synthetic_three_terms_chunked(engine, N, irregular):
+    t, y, yerr = synthetic_star(N, 11)
+    if irregular:
+        rng = np.random.default_rng(5)
+        t = t + rng.uniform(-1e-7, 1e-7, N)         # barycentric-style timing jitter
+        t[N // 3:] += 0.0123                          # odd gap
+    np.random.seed(3)
+    gp = GPModel(C3_CONFIG_GP)
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    theta = np.hstack([gp.sample_prior(16), tr.sample_prior(16)])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want_parts = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    for chunks, halo in ((1, 0), (8, 0), (16, 0), (0, 0), (8, 64)):
+        engine.set_option("chunks", chunks)
+        engine.set_option("halo", halo)
+        lp, parts = engine.log_prob(theta, return_parts=True)
+        assert_parts_close(parts, want_parts)
+    engine.set_option("chunks", 0)
+    engine.set_option("halo", 0)
+    assert np.all(np.isfinite(want_lp))
+
+
+def test_short_halo_is_caught_by_verification(engine):
+    """A deliberately useless halo must be detected and repaired by the exact second pass."""
+    t, y, yerr = synthetic_star(8192, 2)
+    np.random.seed(3)
+    gp = GPModel(C3_CONFIG_GP)
+    spec = build_spec(gp, None)
+    theta = gp.sample_prior(8)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want_parts = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+    engine.set_option("chunks", 16)
+    engine.set_option("halo", 2)
+    before = engine.stat("pass2_chunks")
+    lp, parts = engine.log_prob(theta, return_parts=True)
+    assert engine.stat("pass2_chunks") > before
+    assert_parts_close(parts, want_parts)
+    # with verification off the same setting is visibly wrong: the check is what protects parity
+    engine.set_option("verify", 0)
+    lp2, parts2 = engine.log_prob(theta, return_parts=True)
+    assert rel(parts2[:, 1], want_parts[:, 1]) > 1e-9
+    engine.set_option("verify", 1)
+    engine.set_option("chunks", 0)
+    engine.set_option("halo", 0)
+
+
+def test_edge_cases(engine):
+    # tiny N, single walker, white-noise-only model, transit-only model, Q < 1/2, non-finite input
+    wn = [{"type": "white_noise", "params": {"values": {"jitter": [False, None, "uniform", 1, 300]}}}]
+    for N in (1, 2, 3, 129, 257):
+        t, y, yerr = synthetic_star(N, N)
+        for cfg in (C3_CONFIG_GP[:1] + wn, wn):
+            gp = GPModel(cfg)
+            spec = build_spec(gp, None)
+            np.random.seed(N)
+            theta = gp.sample_prior(3)
+            engine.clear_stars()
+            engine.set_model(spec)
+            engine.upload_star(0, t, y, yerr)
+            _, parts = engine.log_prob(theta, return_parts=True)
+            _, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+            assert_parts_close(parts, want)
+            # known-answer identity: white noise only => independent Gaussians
+            if cfg is wn:
+                var = yerr ** 2 + theta[:, :1] ** 2
+                lnl = -0.5 * np.sum(y ** 2 / var + np.log(var) + np.log(2 * np.pi), axis=1)
+                assert rel(parts[:, 3], lnl) < RTOL
+    # transit only (chi^2, model.py:328-343 with the prior sign fixed)
+    t, y, yerr = synthetic_star(600, 9)
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(None, tr)
+    np.random.seed(1)
+    theta = tr.sample_prior(5)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y - 1e6, yerr)
+    lp, parts = engine.log_prob(theta, return_parts=True)
+    want_lp, want = oracle.log_prob(spec, t, y - 1e6, yerr, theta, return_parts=True)
+    assert rel(lp, want_lp) < RTOL
+    # Q < 1/2: the SHO term splits into two real celerite terms
+    lowq = [{"type": "oscillation_bump", "params": {"values": {"P_g": [False, None, "uniform", 10, 500],
+                                                             "Q": [False, None, "uniform", 0.05, 2.0],
+                                                             "nu_max": [False, None, "uniform", 50, 200]}}}] + wn
+    gp = GPModel(lowq)
+    spec = build_spec(gp, None)
+    theta = np.array([[200.0, 0.3, 120.0, 80.0], [100.0, 0.1, 60.0, 50.0], [300.0, 1.5, 150.0, 90.0],
+                      [300.0, 0.49999, 150.0, 90.0], [np.nan, 1.0, 100.0, 50.0], [300.0, 5.0, 150.0, 90.0]])
+    t, y, yerr = synthetic_star(700, 4)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y - 1e6, yerr)
+    lp, parts = engine.log_prob(theta, return_parts=True)
+    want_lp, want = oracle.log_prob(spec, t, y - 1e6, yerr, theta, return_parts=True)
+    assert lp[4] == -np.inf and want_lp[4] == -np.inf and lp[5] == -np.inf
+    ok = np.isfinite(want_lp)
+    assert rel(lp[ok], want_lp[ok]) < 1e-8      # Q -> 1/2 is ill-conditioned (1/f blows up)
+    assert_parts_close(parts[:3], want[:3])
+
+
+def test_multi_star_batch(engine):
+    np.random.seed(5)
+    gp = GPModel(C3_CONFIG_GP)
+    spec = build_spec(gp, None)
+    engine.clear_stars()
+    engine.set_model(spec)
+    stars = [synthetic_star(1024, 100 + s) for s in range(5)]
+    for s, (t, y, yerr) in enumerate(stars):
+        engine.upload_star(s, t, y, yerr)
+    theta = gp.sample_prior(5 * 6).reshape(5, 6, -1)
+    lp = engine.log_prob(theta, star=0, nstars=5)
+    for s, (t, y, yerr) in enumerate(stars):
+        want = oracle.log_prob(spec, t, y, yerr, theta[s])
+        assert rel(lp[s], want) < RTOL
+    # a sub-range of stars
+    lp2 = engine.log_prob(theta[2:4], star=2, nstars=2)
+    assert np.array_equal(lp2, lp[2:4])
+
+
+def test_sampler_matches_oracle_stream(engine, sim_lc, sim_config):
+    """Same Philox stream, same proposals, same accept decisions: the chains agree step by step."""
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config, "cosi")
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    np.random.seed(42)
+    W, nsteps = 24, 12
+    init = np.hstack([gp.sample_prior(W), tr.sample_prior(W)])
+    init[:, 9] = np.random.uniform(5, 15, W)
+    init[:, 10] = np.random.uniform(0, 0.05, W)
+    chain, logp, nacc = engine.sample(init, nsteps, seed=1234)
+    ochain, ologp, onacc = oracle.sample(spec, t, y, yerr, init, nsteps, seed=1234)
+    assert chain.shape == (W, nsteps, 11) and logp.shape == (nsteps, W)
+    assert np.array_equal(nacc, onacc)
+    assert rel(chain, ochain) < 1e-9
+    fin = np.isfinite(ologp)
+    assert np.array_equal(np.isfinite(logp), fin)
+    assert rel(logp[fin], ologp[fin]) < 1e-9
+    assert 0 < nacc.sum() < W * nsteps
+    # resume: 12 steps == 5 steps + 7 steps from step0=5
+    c1, l1, _ = engine.sample(init, 5, seed=1234)
+    c2, l2, _ = engine.sample(c1[:, -1, :], 7, seed=1234, step0=5)
+    assert np.array_equal(np.concatenate([c1, c2], axis=1), chain)
+
+
+def test_sampler_recovers_gaussian_posterior(engine):
+    """Statistical check: white-noise-only model has a known posterior for the jitter."""
+    rng = np.random.default_rng(0)
+    N = 400
+    t = np.arange(N) * 0.02
+    y = rng.normal(0, 100.0, N)
+    wn = [{"type": "white_noise", "params": {"values": {"jitter": [False, None, "uniform", 1, 1000]}}},
+          {"type": "granulation", "params": {"values": {"a_gran": [False, None, "uniform", 0.01, 50],
+                                                        "b_gran": [False, None, "uniform", 10, 100]}}}]
+    gp = GPModel(wn)
+    spec = build_spec(gp, None)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, np.full(N, 1e-3))
+    np.random.seed(1)
+    W = 32
+    init = gp.sample_prior(W)
+    chain, logp, nacc = engine.sample(init, 600, seed=7)
+    jit = chain[:, 300:, 0].ravel()
+    # jitter posterior ~ sample std of y (the weak granulation term absorbs little)
+    assert abs(np.median(jit) - y.std()) < 8.0
+    acc = nacc.mean() / 600
+    assert 0.1 < acc < 0.8
+
+
+def test_model_surface_runs_kic_example(kic_lc, kic_config, tmp_path):
+    from gptransits_b200 import LightCurve, Model
+    t, f, e = kic_lc
+    cfg = dict(kic_config, settings=dict(kic_config["settings"], num_steps=40, save=True, checkpoint_every=25))
+    lc = LightCurve(t, f * 1e6, e * 1e6)
+    m = Model(lc, cfg, wdir=tmp_path, quiet=True)
+    m.run()
+    assert m.chain.shape == (24, 40, 6) and m.log_prob.shape == (40, 24)
+    assert (tmp_path / "data" / "chain.pk").is_file()
+    lp0 = m.lnlike_func(m.chain[0, -1])
+    assert abs(lp0 - m.log_prob[-1, 0]) <= 1e-9 * abs(lp0)
+    # resume: asking for more steps continues from the stored state
+    cfg2 = dict(cfg, settings=dict(cfg["settings"], num_steps=60))
+    m2 = Model(lc, cfg2, wdir=tmp_path, quiet=True)
+    m2.run()
+    assert m2.chain.shape == (24, 60, 6)
+    assert np.array_equal(m2.chain[:, :40], m.chain)
+    stats = m2.statistics()
+    assert stats["params"]["median"].shape == (6,)
+    m.close()
+    m2.close()
