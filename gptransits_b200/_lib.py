@@ -75,6 +75,12 @@ SIGNATURES = {
     "gpt_sampler_state": (C.c_int, [_vp, _dp, _dp, _i64p]),
     "gpt_sampler_end": (C.c_int, [_vp]),
     "gpt_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+    "gpt_sampler_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "gpt_log_prob_device_timed": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
+                                            C.POINTER(C.c_float)]),
+    "gpt_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "gpt_device_free": (C.c_int, [_vp, _vp]),
+    "gpt_device_copy": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
 }
 
 

@@ -38,6 +38,8 @@ constexpr int PP_TP = 29;      // time of periastron
 constexpr int PP_WCEN = 30;    // transit window centre (days)
 constexpr int PP_WHALF = 31;   // transit window half-width in phase units (>=0.5: everything)
 constexpr int PP_TYPEMASK = 32; // bit k set: term k is a real pair (stored as double)
+constexpr int PP_INVPER = 33;   // 1 / per (window test uses a multiply, identically in every kernel)
+constexpr int PP_MAXCD = 34;    // max |c|, |d| over terms (selects the cadence-jitter series order)
 
 struct ModelDev {
 	int ncomp;
@@ -251,6 +253,7 @@ __device__ inline double ma_flux(double d, double p, double c1, double c2, int m
 			Ek = ellec_dev(q, mode);
 			lambdad = 1.0 / 3.0 + 2.0 / 9.0 / pi * (4.0 * (2.0 * p * p - 1.0) * Ek + (1.0 - 4.0 * p * p) * Kk);
 			etad = p * p / 2.0 * (p * p + 2.0 * d * d);
+			lambdae = p * p;  // batman leaves it unset on this branch; Mandel-Agol value
 		} else if (d > 0.5) {
 			q = 0.5 / p;
 			Kk = ellk_dev(q, mode);
@@ -304,7 +307,7 @@ __device__ inline double ma_flux(double d, double p, double c1, double c2, int m
 struct TransitPars {
 	double per, t0, rp, a, inc, ecc, w, u1, u2;  // batman semantics, angles in radians
 	double tp;                                   // time of periastron (batman _rsky.c)
-	double wcen, whalf;                          // conservative in-transit window
+	double wcen, whalf, inv_per;                 // conservative in-transit window
 };
 
 __device__ inline double kepler_E(double M, double e)
@@ -370,15 +373,25 @@ __device__ inline void transit_window(TransitPars &tr, double exp_time)
 {
 	tr.wcen = tr.t0;
 	tr.whalf = 1.0;
+	tr.inv_per = 1.0 / tr.per;
 	double p = fabs(tr.rp);
 	double rmin = tr.a * (1.0 - tr.ecc);
 	if (!(tr.ecc >= 0.0 && tr.ecc < 0.99) || !(rmin > 0.0) || !(p < 90.0) || !(fabs(tr.per) > 0.0) ||
 	    !isfinite(tr.per) || !isfinite(tr.t0) || !isfinite(tr.w) || !isfinite(tr.inc))
 		return;
 	double sw = (1.0 + p) / rmin * (1.0 + 1e-9);
-	if (!(sw < 1.0)) return;
-	double df = asin(sw);
-	double si = sin(tr.inc);
+	double si = sin(tr.inc), ci = cos(tr.inc);
+	// d = r sqrt(sin^2 psi + cos^2 psi cos^2 i) with psi the angle from conjunction and r >= rmin:
+	// d < 1 + p needs sin^2 psi < (sw^2 - cos^2 i) / sin^2 i
+	double num = sw * sw - ci * ci, den = si * si;
+	if (!(den > 0.0)) return;
+	if (num <= 0.0) {
+		tr.whalf = -1.0;  // never closer than 1 + p: no sample is in transit
+		return;
+	}
+	double s2 = num / den * (1.0 + 1e-9);
+	if (!(s2 < 1.0)) return;
+	double df = asin(sqrt(s2));
 	double fmid = (si >= 0.0 ? 0.5 * kPi : 1.5 * kPi) - tr.w;
 	double Mm = mean_anomaly_of_f(fmid, tr.ecc);
 	double M1 = mean_anomaly_of_f(fmid - df, tr.ecc);
@@ -389,12 +402,16 @@ __device__ inline void transit_window(TransitPars &tr, double exp_time)
 	tr.whalf = half / kTwoPi + fabs(0.5 * exp_time / tr.per) + 1e-9;
 }
 
-__device__ inline bool in_transit_window(double t, const TransitPars &tr)
+__device__ __forceinline__ bool in_transit_window(double t, double wcen, double inv_per, double whalf)
 {
-	if (tr.whalf >= 0.5) return true;
-	double ph = (t - tr.wcen) / tr.per;
+	// |ph| <= 0.5 after the rint, so whalf >= 0.5 means "always"; NaN -> inside (compute, propagate NaN)
+	double ph = (t - wcen) * inv_per;
 	ph -= rint(ph);
-	return !(fabs(ph) > tr.whalf);  // NaN -> inside (compute, propagate NaN like batman)
+	return !(fabs(ph) > whalf);
+}
+__device__ __forceinline__ bool in_transit_window(double t, const TransitPars &tr)
+{
+	return in_transit_window(t, tr.wcen, tr.inv_per, tr.whalf);
 }
 
 // exposure-averaged flux at sample time t (batman supersampling: linspace(-e/2, e/2, s) offsets)

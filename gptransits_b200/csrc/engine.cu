@@ -23,6 +23,8 @@ using namespace gpt;
 		}                                                                                  \
 	} while (0)
 
+enum { TK_PREP = 0, TK_TRANSIT, TK_CHUNK, TK_FINAL, TK_PASS2, TK_TRSCAN, TK_COUNT };
+
 namespace {
 
 template <typename T>
@@ -50,6 +52,7 @@ struct DevBuf {
 
 struct Star {
 	double4 *samp = nullptr;
+	double *tdays = nullptr;
 	int N = 0;
 	double dt0 = 0, dreg = 0, dmax = 0;
 	bool has_err = false;
@@ -73,6 +76,8 @@ struct gpt_engine {
 	int opt_chunks = 0;      // 0 = auto
 	int opt_verify = 1;
 	int opt_halo_auto = 1;
+	int opt_ctas_per_sm = 1;
+	double opt_min_chunk_halos = 0.75;  // chunk length >= this many halos
 	double opt_tol = 1e-11;
 	int cur_halo = 192;
 
@@ -86,7 +91,9 @@ struct gpt_engine {
 	DevBuf<int> d_flags, d_wstatus;
 	DevBuf<ChunkPartial> d_partial;
 	DevBuf<unsigned char> d_redo;
-	DevBuf<int> d_nbad;      // [1] + verr as 2 ints
+	DevBuf<unsigned long long> d_queue;  // transit work queue: (walker << 32) | sample
+	DevBuf<unsigned int> d_qcount;
+	DevBuf<int> d_nbad;      // [1]
 	DevBuf<double> d_verr;   // [1]
 	int *h_nbad = nullptr;   // pinned
 	double *h_verr = nullptr;
@@ -101,6 +108,66 @@ struct gpt_engine {
 	DevBuf<int> s_act, s_ids;
 	DevBuf<long long> s_nacc;
 
+	// running totals written by the finalize kernel: [0] flagged chunks, [1] max error ratio (bits)
+	DevBuf<unsigned long long> d_acc;
+
+	// optional per-kernel CUDA-event timing on the engine stream (option "time_kernels")
+	int opt_time = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[TK_COUNT];
+	std::vector<cudaEvent_t> ev_pool;
+	double t_ms[TK_COUNT] = {0};
+	long long t_n[TK_COUNT] = {0};
+	cudaEvent_t ev_get()
+	{
+		if (!ev_pool.empty()) {
+			cudaEvent_t v = ev_pool.back();
+			ev_pool.pop_back();
+			return v;
+		}
+		cudaEvent_t v;
+		cudaEventCreate(&v);
+		return v;
+	}
+	void timer_begin(int k)
+	{
+		if (!opt_time) return;
+		cudaEvent_t a = ev_get(), b = ev_get();
+		cudaEventRecord(a, stream);
+		tev[k].push_back({a, b});
+	}
+	void timer_end(int k)
+	{
+		if (!opt_time || tev[k].empty()) return;
+		cudaEventRecord(tev[k].back().second, stream);
+	}
+	void timer_collect()
+	{
+		cudaStreamSynchronize(stream);
+		for (int k = 0; k < TK_COUNT; k++) {
+			for (auto &pr : tev[k]) {
+				float ms = 0;
+				if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+					t_ms[k] += ms;
+					t_n[k]++;
+				}
+				ev_pool.push_back(pr.first);
+				ev_pool.push_back(pr.second);
+			}
+			tev[k].clear();
+		}
+	}
+	void adapt_halo(int H, bool failed, double ratio)
+	{
+		if (!opt_halo_auto || opt_halo != 0 || H <= 0) return;
+		// geometric decay model: error/tolerance ratio r at halo H, O(1e12) at H = 0; aim at 1e-2
+		double r = failed ? 1e3 : std::max(ratio, 1e-30);
+		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(1e-2);
+		double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
+		int nh = (int)std::ceil(want / 16.0) * 16;
+		nh = std::max(32, std::min(nh, 4096));
+		cur_halo = nh > cur_halo ? nh : std::max(nh, (int)(cur_halo * 0.9));
+	}
+
 	void set_error(const std::string &m) { err = m; }
 };
 
@@ -111,6 +178,7 @@ static int sync_stars(gpt_engine *e)
 	std::vector<StarDev> h(e->stars.size());
 	for (size_t i = 0; i < h.size(); i++) {
 		h[i].samp = e->stars[i].samp;
+		h[i].tdays = e->stars[i].tdays;
 		h[i].N = e->stars[i].N;
 		h[i]._pad = 0;
 		h[i].dt0 = e->stars[i].dt0;
@@ -149,7 +217,8 @@ static int check_stars(gpt_engine *e, int star0, int nstars)
 	return GPT_OK;
 }
 
-// chunk geometry: enough (walker, chunk) threads to give every SM sub-partition ~2 warps
+// chunk geometry: a whole number of CTA waves over the 148 SMs ("ctas_per_sm" per SM), but never
+// chunks much shorter than the halo they each have to recompute
 static void pick_geometry(gpt_engine *e, int N, int W, int nstars, int &nchunks, int &L, int &H)
 {
 	H = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
@@ -157,17 +226,16 @@ static void pick_geometry(gpt_engine *e, int N, int W, int nstars, int &nchunks,
 	if (e->opt_chunks > 0) {
 		nc = e->opt_chunks;
 	} else {
-		long long warps_per_layer = (long long)nstars * ((W + 31) / 32);
-		long long target = 148LL * 8;
-		nc = (int)std::max<long long>(1, (target + warps_per_layer - 1) / warps_per_layer);
-		int maxc = std::max(1, N / std::max(2 * H, 64));
+		long long ctas_per_layer = (long long)nstars * ((W + CHUNK_THREADS - 1) / CHUNK_THREADS);
+		long long target = 148LL * std::max(1, e->opt_ctas_per_sm);
+		nc = (int)std::max<long long>(1, target / ctas_per_layer);
+		int maxc = std::max(1, (int)(N / std::max(e->opt_min_chunk_halos * H, 64.0)));
 		nc = std::min(nc, maxc);
 	}
 	nc = std::max(1, std::min(nc, N));
 	L = (N + nc - 1) / nc;
 	nchunks = (N + L - 1) / L;
 	if (nchunks == 1) H = 0;
-	H = std::min(H, L);
 }
 
 template <int NT>
@@ -212,18 +280,35 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	CK(e->d_wstatus.ensure(nwalk));
 	CK(e->d_nbad.ensure(1));
 	CK(e->d_verr.ensure(1));
-	if (m.has_transit) CK(e->d_mean.ensure((size_t)nwalk * N));
+	if (!e->d_acc.p) {
+		CK(e->d_acc.ensure(2));
+		CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
+	}
+	if (m.has_transit) {
+		CK(e->d_mean.ensure((size_t)nwalk * N));
+		CK(e->d_queue.ensure((size_t)nwalk * N));
+		CK(e->d_qcount.ensure(1));
+	}
 
 	CK(cudaMemsetAsync(e->d_wstatus.p, 0, sizeof(int) * nwalk, st));
 	CK(cudaMemsetAsync(e->d_nbad.p, 0, sizeof(int), st));
 	CK(cudaMemsetAsync(e->d_verr.p, 0, sizeof(double), st));
+	e->timer_begin(TK_PREP);
 	prep_kernel<<<(nwalk + 127) / 128, 128, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p);
+	e->timer_end(TK_PREP);
 	e->n_launch++;
 	if (m.has_transit) {
 		dim3 g((N + TR_THREADS - 1) / TR_THREADS, nwalk);
-		transit_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode, e->d_prep.p,
-							 e->d_flags.p, e->d_mean.p, 0);
-		e->n_launch++;
+		e->timer_begin(TK_TRANSIT);
+		CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), st));
+		e->timer_begin(TK_TRSCAN);
+		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
+							      e->d_mean.p, 0);
+		e->timer_end(TK_TRSCAN);
+		transit_eval_kernel<<<148 * 4, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode,
+								    e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
+		e->timer_end(TK_TRANSIT);
+		e->n_launch += 2;
 	}
 	e->n_evals += nwalk;
 
@@ -252,10 +337,12 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	ChunkArgs a;
 	a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
 	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
-	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p;
+	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p;
 	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
 	dim3 grid(nchunks, (W + CHUNK_THREADS - 1) / CHUNK_THREADS, nstars);
+	e->timer_begin(TK_CHUNK);
 	launch_chunk(nt, m.has_transit != 0, grid, st, a);
+	e->timer_end(TK_CHUNK);
 	e->n_launch++;
 
 	FinalArgs f;
@@ -264,8 +351,12 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	f.nbad = e->d_nbad.p; f.lp = d_lp; f.parts = d_parts; f.verr = e->d_verr.p;
 	f.nwalk = nwalk; f.N = N; f.nchunks = nchunks; f.H = H; f.nterms = nt;
 	f.verify = (nchunks > 1 && e->opt_verify) ? 1 : 0;
+	f.skip_if_clean = 0;
+	f.acc = e->d_acc.p;
 	f.tol = e->opt_tol;
+	e->timer_begin(TK_FINAL);
 	gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+	e->timer_end(TK_FINAL);
 	e->n_launch++;
 
 	if (e->may_generic) {
@@ -289,24 +380,18 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 				e->n_pass2_calls++;
 				e->n_pass2_chunks += *e->h_nbad;
 			}
-			if (e->opt_halo_auto && e->opt_halo == 0) {
-				// geometric decay model: ratio r at halo H, O(1e12) at H = 0
-				double r = need ? 1e3 : std::max(e->last_verr, 1e-30);
-				double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(1e-2);
-				double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
-				int nh = (int)std::ceil(want / 16.0) * 16;
-				nh = std::max(32, std::min(nh, 4096));
-				if (nh > e->cur_halo)
-					e->cur_halo = nh;
-				else
-					e->cur_halo = std::max(nh, (int)(e->cur_halo * 0.9));
-			}
+			e->adapt_halo(H, need, e->last_verr);
 		}
 		if (need) {
+			// pass 2 exits at once on the device when nothing was flagged, so the asynchronous
+			// path can enqueue it unconditionally (no host round trip inside a sampler step)
 			a.pass2 = 1;
+			e->timer_begin(TK_PASS2);
 			launch_chunk(nt, m.has_transit != 0, grid, st, a);
 			f.verify = 0;
+			f.skip_if_clean = 1;
 			gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+			e->timer_end(TK_PASS2);
 			e->n_launch += 2;
 		}
 	}
@@ -345,8 +430,10 @@ int gpt_star_clear(gpt_engine *e)
 	if (!e) return GPT_E_INVALID;
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
-	for (auto &s : e->stars)
+	for (auto &s : e->stars) {
 		if (s.samp) cudaFree(s.samp);
+		if (s.tdays) cudaFree(s.tdays);
+	}
 	e->stars.clear();
 	e->stars_dirty = true;
 	return GPT_OK;
@@ -361,7 +448,8 @@ void gpt_engine_destroy(gpt_engine *e)
 	e->d_stars.release();
 	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
 	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
-	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release();
+	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
+	e->d_queue.release(); e->d_qcount.release();
 	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
 	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
 	if (e->h_nbad) cudaFreeHost(e->h_nbad);
@@ -382,10 +470,23 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_chunks = (int)value;
 	} else if (k == "verify") {
 		e->opt_verify = value != 0;
+	} else if (k == "ctas_per_sm") {
+		e->opt_ctas_per_sm = std::max(1, (int)value);
+	} else if (k == "min_chunk_halos") {
+		e->opt_min_chunk_halos = value;
 	} else if (k == "halo_auto") {
 		e->opt_halo_auto = value != 0;
 	} else if (k == "verify_tol") {
 		e->opt_tol = value;
+	} else if (k == "time_kernels") {
+		e->opt_time = value != 0;
+		if (!e->opt_time) e->timer_collect();
+	} else if (k == "reset_timers") {
+		e->timer_collect();
+		for (int i = 0; i < TK_COUNT; i++) {
+			e->t_ms[i] = 0;
+			e->t_n[i] = 0;
+		}
 	} else if (k == "halo_start") {
 		e->cur_halo = std::max(0, (int)value);
 	} else {
@@ -409,6 +510,27 @@ int gpt_get_stat(gpt_engine *e, const char *key, double *value)
 	else if (k == "halo") *value = e->last_H;
 	else if (k == "halo_next") *value = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
 	else if (k == "nstars") *value = (double)e->stars.size();
+	else if (k == "transit_items") {
+		unsigned int q = 0;
+		if (e->d_qcount.p) {
+			cudaStreamSynchronize(e->stream);
+			cudaMemcpy(&q, e->d_qcount.p, sizeof(q), cudaMemcpyDeviceToHost);
+		}
+		*value = q;
+	}
+	else if (k.rfind("ms_", 0) == 0 || k.rfind("n_", 0) == 0) {
+		static const char *names[TK_COUNT] = {"prep", "transit", "chunk", "final", "pass2", "trscan"};
+		e->timer_collect();
+		bool ms = k[0] == 'm';
+		std::string which = k.substr(ms ? 3 : 2);
+		for (int i = 0; i < TK_COUNT; i++)
+			if (which == names[i]) {
+				*value = ms ? e->t_ms[i] : (double)e->t_n[i];
+				return GPT_OK;
+			}
+		e->set_error("unknown stat: " + k);
+		return GPT_E_INVALID;
+	}
 	else {
 		e->set_error("unknown stat: " + k);
 		return GPT_E_INVALID;
@@ -495,7 +617,9 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	Star &s = e->stars[star];
 	CK(cudaStreamSynchronize(e->stream));
 	if (s.samp) cudaFree(s.samp);
+	if (s.tdays) cudaFree(s.tdays);
 	s.samp = nullptr;
+	s.tdays = nullptr;
 	std::vector<double4> h(N);
 	std::vector<double> dts;
 	dts.reserve(N);
@@ -527,6 +651,8 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	s.has_err = yerr != nullptr;
 	CK(cudaMalloc((void **)&s.samp, sizeof(double4) * N));
 	CK(cudaMemcpy(s.samp, h.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
+	CK(cudaMalloc((void **)&s.tdays, sizeof(double) * N));
+	CK(cudaMemcpy(s.tdays, t_days, sizeof(double) * N, cudaMemcpyHostToDevice));
 	e->stars_dirty = true;
 	return GPT_OK;
 }
@@ -586,13 +712,19 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 	CK(e->d_prep.ensure((size_t)W * PREP_STRIDE));
 	CK(e->d_flags.ensure(W));
 	CK(e->d_mean.ensure((size_t)W * N));
+	CK(e->d_queue.ensure((size_t)W * N));
+	CK(e->d_qcount.ensure(1));
+	CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), e->stream));
 	CK(cudaMemcpyAsync(e->d_theta.p, pars9, sizeof(double) * W * 9, cudaMemcpyHostToDevice, e->stream));
 	prep_transit_direct_kernel<<<(W + 127) / 128, 128, 0, e->stream>>>(e->model.exp_time, e->d_theta.p, W, e->d_prep.p,
 									    e->d_flags.p);
 	dim3 g((N + TR_THREADS - 1) / TR_THREADS, W);
-	transit_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample, e->model.exp_time,
-							e->model.ellip_mode, e->d_prep.p, e->d_flags.p, e->d_mean.p, 1);
-	e->n_launch += 2;
+	transit_scan_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
+							     e->d_qcount.p, e->d_mean.p, 1);
+	transit_eval_kernel<<<148 * 4, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample,
+								   e->model.exp_time, e->model.ellip_mode, e->d_prep.p,
+								   e->d_queue.p, e->d_qcount.p, e->d_mean.p, 1);
+	e->n_launch += 3;
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(flux, e->d_mean.p, sizeof(double) * (size_t)W * N, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
@@ -647,7 +779,7 @@ int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_
 	return GPT_OK;
 }
 
-int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep)
+static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l2, float *ms_per_step)
 {
 	if (!e || nsteps < 0) return GPT_E_INVALID;
 	if (!e->sampling) {
@@ -668,13 +800,27 @@ int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep)
 	}
 	cudaStream_t st = e->stream;
 	const int nh = ns * H;
+	std::vector<cudaEvent_t> ev;
+	DevBuf<char> flush;
+	const size_t flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+	if (ms_per_step) {
+		ev.resize(2 * nsteps);
+		for (auto &v : ev) CK(cudaEventCreate(&v));
+		if (flush_l2) CK(flush.ensure(flush_bytes));
+	}
+	CK(e->d_acc.ensure(2));
+	CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
 	for (int64_t s = 0; s < nsteps; s++) {
+		if (ms_per_step) {
+			if (flush_l2) CK(cudaMemsetAsync(flush.p, (int)(s & 0xff), flush_bytes, st));
+			CK(cudaEventRecord(ev[2 * s], st));
+		}
 		sampler_split_kernel<<<ns, 256, (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st>>>(S, e->s_step);
 		e->n_launch++;
 		for (int half = 0; half < 2; half++) {
 			sampler_propose_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
 			e->n_launch++;
-			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, true);
+			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false);
 			if (rc) return rc;
 			sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
 			e->n_launch++;
@@ -684,10 +830,86 @@ int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep)
 			e->n_launch++;
 			e->s_kept++;
 		}
+		if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
 		e->s_step++;
 	}
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
+	if (ms_per_step) {
+		for (int64_t s = 0; s < nsteps; s++) {
+			CK(cudaEventElapsedTime(&ms_per_step[s], ev[2 * s], ev[2 * s + 1]));
+		}
+		for (auto &v : ev) cudaEventDestroy(v);
+		flush.release();
+	}
+	// verification verdicts accumulated on the device over this block of steps
+	if (e->d_acc.p && nsteps > 0) {
+		unsigned long long acc[2] = {0, 0};
+		CK(cudaMemcpy(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost));
+		double ratio;
+		memcpy(&ratio, &acc[1], sizeof(double));
+		e->last_verr = ratio;
+		if (acc[0]) {
+			e->n_pass2_calls++;
+			e->n_pass2_chunks += (long long)acc[0];
+		}
+		e->adapt_halo(e->last_H, acc[0] > 0, ratio);
+	}
+	return GPT_OK;
+}
+
+int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep) { return sampler_run_impl(e, nsteps, keep, 0, nullptr); }
+
+int gpt_sampler_run_timed(gpt_engine *e, int64_t nsteps, int keep, int flush_l2, float *ms_per_step)
+{
+	if (!ms_per_step) return GPT_E_INVALID;
+	return sampler_run_impl(e, nsteps, keep, flush_l2, ms_per_step);
+}
+
+int gpt_log_prob_device_timed(gpt_engine *e, int star0, int nstars, const double *theta_device, int W,
+			      double *lp_device, int reps, int flush_l2, float *ms_per_rep)
+{
+	if (!e || !theta_device || !lp_device || W < 1 || reps < 1 || !ms_per_rep) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	std::vector<cudaEvent_t> ev(2 * reps);
+	for (auto &v : ev) CK(cudaEventCreate(&v));
+	DevBuf<char> flush;
+	const size_t flush_bytes = (size_t)256 << 20;
+	if (flush_l2) CK(flush.ensure(flush_bytes));
+	for (int r = 0; r < reps; r++) {
+		if (flush_l2) CK(cudaMemsetAsync(flush.p, r & 0xff, flush_bytes, e->stream));
+		CK(cudaEventRecord(ev[2 * r], e->stream));
+		int rc = eval_enqueue(e, star0, nstars, theta_device, W, lp_device, nullptr, false);
+		if (rc) return rc;
+		CK(cudaEventRecord(ev[2 * r + 1], e->stream));
+	}
+	CK(cudaStreamSynchronize(e->stream));
+	for (int r = 0; r < reps; r++) CK(cudaEventElapsedTime(&ms_per_rep[r], ev[2 * r], ev[2 * r + 1]));
+	for (auto &v : ev) cudaEventDestroy(v);
+	flush.release();
+	return GPT_OK;
+}
+
+int gpt_device_alloc(gpt_engine *e, size_t bytes, void **out)
+{
+	if (!e || !out) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	CK(cudaMalloc(out, bytes));
+	return GPT_OK;
+}
+int gpt_device_free(gpt_engine *e, void *p)
+{
+	if (!e) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	CK(cudaFree(p));
+	return GPT_OK;
+}
+int gpt_device_copy(gpt_engine *e, void *dst, const void *src, size_t bytes, int to_device)
+{
+	if (!e) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	CK(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
 	return GPT_OK;
 }
 

@@ -58,6 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // ------------------------------------------------------------------ device-side descriptors
 struct StarDev {
 	const double4 *samp;  // [N] {dt_ms, y, var, t_days}
+	const double *tdays;  // [N] compact copy of the sample times (transit window scan)
 	int N;
 	int _pad;
 	double dt0;    // base cadence (megaseconds)
@@ -139,6 +140,7 @@ __global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const doubl
 	// the series used on regular steps need |c * ddt|, |d * ddt| <= 1e-3
 	if (!(maxcd * st.dmax <= 1.0e-3)) fl |= WF_SLOWTRIG;
 	pp[PP_JIT2] = jit2;
+	pp[PP_MAXCD] = maxcd;
 	pp[PP_ASUM] = jit2 + asum;
 	pp[PP_TYPEMASK] = (double)typemask;
 
@@ -167,6 +169,7 @@ __global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const doubl
 		pp[PP_TP] = tr.tp;
 		pp[PP_WCEN] = tr.wcen;
 		pp[PP_WHALF] = tr.whalf;
+		pp[PP_INVPER] = tr.inv_per;
 		if (tr.whalf >= 0.5) fl |= WF_TR_ALL;
 	}
 	flags[gw] = fl;
@@ -180,6 +183,7 @@ __device__ inline void load_transit(const double *pp, TransitPars &tr)
 	tr.tp = pp[PP_TP];
 	tr.wcen = pp[PP_WCEN];
 	tr.whalf = pp[PP_WHALF];
+	tr.inv_per = pp[PP_INVPER];
 }
 
 // Direct batman-semantics parameters (gpt_transit_flux): pars9 [nwalk][9] -> prep rows
@@ -207,72 +211,106 @@ __global__ void prep_transit_direct_kernel(double exp_time, const double *pars9,
 	pp[PP_TP] = tr.tp;
 	pp[PP_WCEN] = tr.wcen;
 	pp[PP_WHALF] = tr.whalf;
+	pp[PP_INVPER] = tr.inv_per;
 	flags[gw] = WF_VALID | (tr.whalf >= 0.5 ? WF_TR_ALL : 0);
 }
 
 // ================================================================== transit
-// grid (ceil(N/256), nwalk).  Each block tests 256 consecutive samples of one walker against the
-// walker's transit window, compacts the in-window samples, then spreads (sample, supersample) pairs
-// over all threads so the expensive Mandel-Agol branch runs with dense lanes.
-// dense == 0: writes mean_ppm[gw][n] = (flux-1)*1e6 for in-window samples only (consumed by the GP
-//             kernels, which repeat the identical window test);
-// dense == 1: writes flux[gw][n] for every sample (gpt_transit_flux).
+// Two phases so that the expensive Mandel-Agol branch runs with dense lanes:
+//   transit_scan_kernel  one thread per (walker, sample): window test on the compact time array;
+//                        in-window pairs are appended to a global queue (warp-aggregated atomics)
+//   transit_eval_kernel  persistent grid-stride loop over (queue item, supersample) tasks; the
+//                        supersamples of one item sit in adjacent lanes and are summed in
+//                        np.mean's order by the group's first lane
+// dense == 0: mean_ppm[gw][n] = (flux-1)*1e6 is written for in-window samples only (the GP kernels
+//             repeat the identical window test before reading it);
+// dense == 1: flux[gw][n] is written for every sample (gpt_transit_flux).
 constexpr int TR_THREADS = 256;
-constexpr int TR_FLBUF = 2048;
 
 __global__ void __launch_bounds__(TR_THREADS)
-transit_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep, const int *flags,
-	       double *out, int dense)
+transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
+		    unsigned int *qcount, double *out, int dense)
 {
-	__shared__ int s_cnt;
-	__shared__ short s_list[TR_THREADS];
-	__shared__ double s_fl[TR_FLBUF];
 	const int gw = blockIdx.y;
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
 	const StarDev st = stars[gw / W];
 	const int N = st.N;
 	const int n = blockIdx.x * TR_THREADS + threadIdx.x;
+	const double *pp = prep + (size_t)gw * PREP_STRIDE;
 	TransitPars tr;
-	load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
-	if (threadIdx.x == 0) s_cnt = 0;
-	__syncthreads();
-	double t = 0.0;
+	tr.per = pp[PP_TR + 0];
+	tr.wcen = pp[PP_WCEN];
+	tr.whalf = pp[PP_WHALF];
+	tr.inv_per = pp[PP_INVPER];
 	bool inw = false;
 	if (n < N) {
-		t = st.samp[n].w;
-		inw = in_transit_window(t, tr);
-		if (inw) {
-			int pos = atomicAdd(&s_cnt, 1);
-			s_list[pos] = (short)threadIdx.x;
-		} else if (dense) {
-			out[(size_t)gw * N + n] = 1.0;
-		}
+		inw = in_transit_window(st.tdays[n], tr);
+		if (!inw && dense) out[(size_t)gw * N + n] = 1.0;
 	}
-	__syncthreads();
-	const int cnt = s_cnt;
-	if (cnt == 0) return;
+	const unsigned mask = __ballot_sync(0xffffffffu, inw);
+	if (mask == 0) return;
+	const int lane = threadIdx.x & 31;
+	unsigned int base = 0;
+	if (lane == 0) base = atomicAdd(qcount, (unsigned int)__popc(mask));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (inw) queue[base + __popc(mask & ((1u << lane) - 1))] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n;
+}
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep,
+		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense)
+{
 	if (ss < 1) ss = 1;
-	const int per_batch = TR_FLBUF / ss;
-	for (int base = 0; base < cnt; base += per_batch) {
-		int nb = min(per_batch, cnt - base);
-		for (int task = threadIdx.x; task < nb * ss; task += TR_THREADS) {
-			int item = task / ss, i = task - item * ss;
-			int ln = s_list[base + item];
-			double tn = st.samp[blockIdx.x * TR_THREADS + ln].w;
-			double ts = supersample_time(tn, i, ss, exp_time);
-			double d = rsky_one(ts, tr);
-			s_fl[item * ss + i] = ma_flux(d, tr.rp, tr.u1, tr.u2, mode);
+	const unsigned int nitems = *qcount;
+	const int lane = threadIdx.x & 31;
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int nwarps = (gridDim.x * blockDim.x) >> 5;
+	if (ss <= 32) {
+		const int per_warp = 32 / ss;             // items handled by one warp per iteration
+		const int grp = lane / ss, i = lane - grp * ss;
+		const bool lane_used = grp < per_warp;
+		for (unsigned int first = (unsigned)warp * per_warp; first < nitems; first += (unsigned)nwarps * per_warp) {
+			const unsigned int item = first + grp;
+			const bool on = lane_used && item < nitems;
+			double f = 0.0;
+			int gw = 0, n = 0, N = 0;
+			if (on) {
+				const unsigned long long q = queue[item];
+				gw = (int)(q >> 32);
+				n = (int)(q & 0xffffffffu);
+				const StarDev st = stars[gw / W];
+				N = st.N;
+				TransitPars tr;
+				load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
+				const double ts = supersample_time(st.tdays[n], i, ss, exp_time);
+				f = ma_flux(rsky_one(ts, tr), tr.rp, tr.u1, tr.u2, mode);
+			}
+			// ordered sum over the group's lanes (np.mean order), gathered by the group's first lane
+			double s = f;
+			for (int k = 1; k < ss; k++) {
+				double v = __shfl_down_sync(0xffffffffu, f, k);
+				if (i == 0) s += v;
+			}
+			if (on && i == 0) {
+				double m = ss > 1 ? s / ss : s;
+				out[(size_t)gw * N + n] = dense ? m : (m - 1) * 1e6;  // transit.py:127
+			}
 		}
-		__syncthreads();
-		for (int item = threadIdx.x; item < nb; item += TR_THREADS) {
+	} else {
+		// very large supersampling factors: one lane per item, sequential over supersamples
+		for (unsigned int item = blockIdx.x * blockDim.x + threadIdx.x; item < nitems; item += gridDim.x * blockDim.x) {
+			const unsigned long long q = queue[item];
+			const int gw = (int)(q >> 32), n = (int)(q & 0xffffffffu);
+			const StarDev st = stars[gw / W];
+			TransitPars tr;
+			load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
 			double s = 0.0;
-			for (int i = 0; i < ss; i++) s += s_fl[item * ss + i];  // np.mean order
-			double f = ss > 1 ? s / ss : s;
-			int nn = blockIdx.x * TR_THREADS + s_list[base + item];
-			out[(size_t)gw * N + nn] = dense ? f : (f - 1) * 1e6;  // transit.py:127
+			for (int i = 0; i < ss; i++)
+				s += ma_flux(rsky_one(supersample_time(st.tdays[n], i, ss, exp_time), tr), tr.rp, tr.u1, tr.u2, mode);
+			double m = s / ss;
+			out[(size_t)gw * st.N + n] = dense ? m : (m - 1) * 1e6;
 		}
-		__syncthreads();
 	}
 }
 
@@ -287,6 +325,7 @@ struct ChunkArgs {
 	ChunkPartial *partial;    // [nwalk][nchunks]
 	int *wstatus;             // [nwalk] OR of WF_NOTPD
 	const unsigned char *redo;  // [nwalk][nchunks] (pass 2)
+	const int *nbad;          // [1] pass 2 exits at once when zero
 	int W;                    // walkers per star
 	int N, nchunks, L, H;
 	int pass2;
@@ -317,6 +356,21 @@ __device__ __forceinline__ void sincos_small(double x, double &s, double &c)
 	s = x * fma(x2, fma(x2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
 }
 
+// 1/d by MUFU.RCP64H + two Newton steps (<= 2 ulp), no special-case branch; callers guard d > 0
+__device__ __forceinline__ double fast_rcp(double d)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+	double e = fma(-d, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-d, r, 1.0);
+	return fma(r, e, r);
+}
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 template <int NT, bool TRANSIT>
 __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 {
@@ -336,6 +390,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 	const int n0 = c * A.L;
 	const int n1 = min(N, n0 + A.L);
 	const bool pass2 = A.pass2 != 0;
+	if (pass2 && *A.nbad == 0) return;
 	const int hs = pass2 ? n0 : max(0, n0 - A.H);
 
 	int fl = 0;
@@ -350,8 +405,9 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 
 	// ---- walker coefficients -> registers
 	WalkerCoef<NT> K;
-	TransitPars tr;
-	const bool slow = (fl & WF_SLOWTRIG) != 0;
+	double wcen = 0.0, inv_per = 1.0, whalf = -1.0;  // inactive threads: never in window
+	double dreg = -1.0;                             // |ddt| <= dreg: series for exp / rotation
+	bool tiny = true;                               // first-order series is exact to double precision
 	if (active) {
 		const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
 		K.asum = pp[PP_ASUM];
@@ -364,7 +420,13 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			K.phi0[k] = exp(-K.c[k] * st.dt0);
 			sincos(K.d[k] * st.dt0, &K.sr0[k], &K.cr0[k]);
 		}
-		if (TRANSIT) load_transit(pp, tr);
+		if (TRANSIT) {
+			wcen = pp[PP_WCEN];
+			inv_per = pp[PP_INVPER];
+			whalf = pp[PP_WHALF];
+		}
+		if (!(fl & WF_SLOWTRIG)) dreg = st.dreg;
+		tiny = pp[PP_MAXCD] * st.dmax <= 1.0e-9;
 	} else {
 		K.asum = 1.0;
 #pragma unroll
@@ -374,12 +436,11 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			K.cr0[k] = 1.0;
 			K.sr0[k] = 0.0;
 		}
-		if (TRANSIT) {
-			tr.per = 1.0; tr.wcen = 0.0; tr.whalf = -1.0;  // never in window
-			tr.t0 = tr.rp = tr.a = tr.inc = tr.ecc = tr.w = tr.u1 = tr.u2 = tr.tp = 0.0;
-		}
 	}
+	// block-uniform choice of the series order on regular steps
+	const bool all_tiny = __syncthreads_and(tiny) != 0;
 	const double *meanw = TRANSIT ? (A.mean + (size_t)gw * N) : nullptr;
+	if (!TRANSIT || !(w < A.W)) meanw = nullptr;
 
 	// ---- state
 	double P[NP], g[J], cs[NT], sn[NT];
@@ -421,6 +482,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 	if (threadIdx.x == 0) {
 		for (int tl = t_first; tl <= t_last && tl < t_first + NSTAGE; tl++) issue(tl);
 	}
+	if (TRANSIT && meanw) {
+		prefetch_l1(meanw + hs);
+		prefetch_l1(meanw + min(hs + 16, N - 1));
+	}
 
 	for (int tl = t_first; tl <= t_last; tl++) {
 		const int it = tl - t_first;
@@ -448,59 +513,76 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			const double dt = sm.x;
 			double y = sm.y;
 			if (TRANSIT) {
-				if (in_transit_window(sm.w, tr)) y -= meanw[n];
+				// the transit model of this walker: valid only inside its window, so load
+				// unconditionally (L1-prefetched two lines ahead) and select
+				double mv = 0.0;
+				if (meanw) {
+					mv = meanw[n];
+					if ((n & 15) == 0) prefetch_l1(meanw + min(n + 32, N - 1));
+				}
+				const bool inw = in_transit_window(sm.w, wcen, inv_per, whalf);
+				y -= inw ? mv : 0.0;
 			}
-			// ---- phi, rotation, U, V
+			// ---- phi, rotation
 			double phi[NT], U[J];
 			const double ddt = dt - st.dt0;
-			if (n != s0) {
-				if (!slow && ddt == 0.0) {
+			const bool anchored = (n == s0);
+			if (ddt == 0.0 && dreg >= 0.0) {
 #pragma unroll
-					for (int k = 0; k < NT; k++) {
-						phi[k] = K.phi0[k];
+				for (int k = 0; k < NT; k++) {
+					phi[k] = K.phi0[k];
+					if (!anchored) {
 						double cn = cs[k] * K.cr0[k] - sn[k] * K.sr0[k];
 						double sx = sn[k] * K.cr0[k] + cs[k] * K.sr0[k];
 						cs[k] = cn;
 						sn[k] = sx;
 					}
-				} else if (!slow && fabs(ddt) <= st.dreg) {
+				}
+			} else if (fabs(ddt) <= dreg) {
+				if (all_tiny) {
+					// |c ddt|, |d ddt| <= 1e-9: first order is exact to double precision
+#pragma unroll
+					for (int k = 0; k < NT; k++) {
+						phi[k] = fma(-K.phi0[k], K.c[k] * ddt, K.phi0[k]);
+						if (!anchored) {
+							double xd = K.d[k] * ddt;
+							double cr = fma(-K.sr0[k], xd, K.cr0[k]);
+							double sr = fma(K.cr0[k], xd, K.sr0[k]);
+							double cn = cs[k] * cr - sn[k] * sr;
+							double sx = sn[k] * cr + cs[k] * sr;
+							cs[k] = cn;
+							sn[k] = sx;
+						}
+					}
+				} else {
 #pragma unroll
 					for (int k = 0; k < NT; k++) {
 						phi[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);
-						double s1_, c1_;
-						sincos_small(K.d[k] * ddt, s1_, c1_);
-						double cr = K.cr0[k] * c1_ - K.sr0[k] * s1_;
-						double sr = K.sr0[k] * c1_ + K.cr0[k] * s1_;
-						double cn = cs[k] * cr - sn[k] * sr;
-						double sx = sn[k] * cr + cs[k] * sr;
-						cs[k] = cn;
-						sn[k] = sx;
-					}
-				} else {
-					double x = sm.w * kDaysToMs;
-#pragma unroll
-					for (int k = 0; k < NT; k++) {
-						phi[k] = exp(-K.c[k] * dt);
-						sincos(K.d[k] * x, &sn[k], &cs[k]);
+						if (!anchored) {
+							double s1_, c1_;
+							sincos_small(K.d[k] * ddt, s1_, c1_);
+							double cr = K.cr0[k] * c1_ - K.sr0[k] * s1_;
+							double sr = K.sr0[k] * c1_ + K.cr0[k] * s1_;
+							double cn = cs[k] * cr - sn[k] * sr;
+							double sx = sn[k] * cr + cs[k] * sr;
+							cs[k] = cn;
+							sn[k] = sx;
+						}
 					}
 				}
 			} else {
-				// anchored sample: rotation already absolute; phi from dt
-				if (!slow && ddt == 0.0) {
+				// gap or irregular cadence: direct exp, absolute sincos
+				const double x = sm.w * kDaysToMs;
 #pragma unroll
-					for (int k = 0; k < NT; k++) phi[k] = K.phi0[k];
-				} else if (!slow && fabs(ddt) <= st.dreg) {
-#pragma unroll
-					for (int k = 0; k < NT; k++) phi[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);
-				} else {
-#pragma unroll
-					for (int k = 0; k < NT; k++) phi[k] = exp(-K.c[k] * dt);
+				for (int k = 0; k < NT; k++) {
+					phi[k] = exp(-K.c[k] * dt);
+					if (!anchored) sincos(K.d[k] * x, &sn[k], &cs[k]);
 				}
 			}
 #pragma unroll
 			for (int k = 0; k < NT; k++) {
-				U[2 * k] = K.a[k] * cs[k] + K.b[k] * sn[k];
-				U[2 * k + 1] = K.a[k] * sn[k] - K.b[k] * cs[k];
+				U[2 * k] = fma(K.a[k], cs[k], K.b[k] * sn[k]);
+				U[2 * k + 1] = fma(K.a[k], sn[k], -(K.b[k] * cs[k]));
 			}
 			// ---- S = phi phi^T o P  (in place), f = phi o g
 			double pp_[NT * (NT + 1) / 2];
@@ -515,29 +597,36 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			double f[J];
 #pragma unroll
 			for (int i = 0; i < J; i++) f[i] = phi[i / 2] * g[i];
-			// ---- t = S U ; D = A - U.t
+			// ---- t = S U (two partial sums per row), D = A - U.t, z = y - U.f (pairwise trees)
 			double tv[J];
 #pragma unroll
 			for (int i = 0; i < J; i++) {
-				double acc = 0.0;
+				double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-				for (int j = 0; j < J; j++) {
-					double sij = (i <= j) ? P[tri(i, j, J)] : P[tri(j, i, J)];
-					acc = fma(sij, U[j], acc);
+				for (int j = 0; j < J; j += 2) {
+					double s0_ = (i <= j) ? P[tri(i, j, J)] : P[tri(j, i, J)];
+					double s1_ = (i <= j + 1) ? P[tri(i, j + 1, J)] : P[tri(j + 1, i, J)];
+					acc0 = fma(s0_, U[j], acc0);
+					acc1 = fma(s1_, U[j + 1], acc1);
 				}
-				tv[i] = acc;
+				tv[i] = acc0 + acc1;
 			}
-			double D = sm.z + K.asum;
-			double ut = 0.0, zp = 0.0;
+			double utp[NT], zpp[NT];
 #pragma unroll
-			for (int i = 0; i < J; i++) {
-				ut = fma(U[i], tv[i], ut);
-				zp = fma(U[i], f[i], zp);
+			for (int k = 0; k < NT; k++) {
+				utp[k] = fma(U[2 * k], tv[2 * k], U[2 * k + 1] * tv[2 * k + 1]);
+				zpp[k] = fma(U[2 * k], f[2 * k], U[2 * k + 1] * f[2 * k + 1]);
 			}
-			D -= ut;
+			double ut = utp[0], zp = zpp[0];
+#pragma unroll
+			for (int k = 1; k < NT; k++) {
+				ut += utp[k];
+				zp += zpp[k];
+			}
+			const double D = (sm.z + K.asum) - ut;
 			const double z = y - zp;
 			notpd |= !(D > 0.0);
-			const double invD = 1.0 / D;
+			const double invD = fast_rcp(D);
 			// ---- w = (V - t)/D ; P' = S + D w w^T ; g' = f + w z
 			double wv[J];
 #pragma unroll
@@ -547,7 +636,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			}
 #pragma unroll
 			for (int i = 0; i < J; i++) {
-				double dwi = D * wv[i];
+				// D w_i = V_i - t_i exactly as computed above, before the division
+				double dwi = (i & 1) ? (sn[i / 2] - tv[i]) : (cs[i / 2] - tv[i]);
 #pragma unroll
 				for (int j = i; j < J; j++) P[tri(i, j, J)] = fma(dwi, wv[j], P[tri(i, j, J)]);
 				g[i] = fma(wv[i], z, f[i]);
@@ -605,6 +695,8 @@ struct FinalArgs {
 	double *verr;   // [1] max error/tolerance ratio seen (as double bits via atomicMax on ull)
 	int nwalk, N, nchunks, H, nterms;
 	int verify;     // 1: compare carries and flag chunks; 0: just reduce
+	int skip_if_clean;  // second invocation: nothing to do when pass 1 flagged no chunk
+	unsigned long long *acc;  // [2] running totals over calls: flagged chunks, max error ratio (bits)
 	double tol;
 };
 
@@ -614,6 +706,7 @@ __global__ void gp_finalize_kernel(FinalArgs A)
 	const int lane = threadIdx.x & 31;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= A.nwalk) return;
+	if (A.skip_if_clean && *A.nbad == 0) return;
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
 	if (!(fl & WF_VALID)) {
@@ -677,8 +770,12 @@ __global__ void gp_finalize_kernel(FinalArgs A)
 			worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
 		}
 		if (lane == 0) {
-			if (nbad) atomicAdd(A.nbad, nbad);
+			if (nbad) {
+				atomicAdd(A.nbad, nbad);
+				atomicAdd(A.acc, (unsigned long long)nbad);
+			}
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
+			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
 	}
 	if (lane == 0) {

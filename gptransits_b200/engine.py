@@ -180,3 +180,29 @@ class Engine:
         v = C.c_double()
         self._ck(self._lib.gpt_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+    # -- measurement helpers (bench.py)
+    def sampler_run_timed(self, nsteps, keep=False, flush_l2=True):
+        """-> per-step milliseconds (CUDA events on the engine stream)."""
+        ms = (C.c_float * int(nsteps))()
+        self._ck(self._lib.gpt_sampler_run_timed(self._h, int(nsteps), 1 if keep else 0, 1 if flush_l2 else 0, ms))
+        return np.array(ms[:], dtype=np.float64)
+
+    def log_prob_resident_timed(self, theta, reps, star=0, nstars=1, flush_l2=True):
+        """Upload theta once, evaluate it `reps` times from HBM.  -> (lp, ms per rep)."""
+        flat = _d(theta).reshape(-1, self.ndim)
+        W = flat.shape[0] // nstars
+        d_theta, d_lp = C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.gpt_device_alloc(self._h, flat.nbytes, C.byref(d_theta)))
+        self._ck(self._lib.gpt_device_alloc(self._h, flat.shape[0] * 8, C.byref(d_lp)))
+        try:
+            self._ck(self._lib.gpt_device_copy(self._h, d_theta, flat.ctypes.data_as(C.c_void_p), flat.nbytes, 1))
+            ms = (C.c_float * int(reps))()
+            self._ck(self._lib.gpt_log_prob_device_timed(self._h, int(star), int(nstars), d_theta, W, d_lp,
+                                                         int(reps), 1 if flush_l2 else 0, ms))
+            lp = np.empty(flat.shape[0])
+            self._ck(self._lib.gpt_device_copy(self._h, lp.ctypes.data_as(C.c_void_p), d_lp, lp.nbytes, 0))
+        finally:
+            self._lib.gpt_device_free(self._h, d_theta)
+            self._lib.gpt_device_free(self._h, d_lp)
+        return lp, np.array(ms[:], dtype=np.float64)

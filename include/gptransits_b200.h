@@ -24,6 +24,7 @@
 #ifndef GPTRANSITS_B200_H
 #define GPTRANSITS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -146,6 +147,18 @@ int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep);
 int gpt_sampler_read(gpt_engine *e, int64_t first, int64_t count, double *chain, double *logp);
 int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *naccept);
 int gpt_sampler_end(gpt_engine *e);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------ */
+/* gpt_sampler_run with one CUDA-event pair per step on the engine's stream; flush_l2 != 0
+ * overwrites a 256 MiB buffer between steps (outside the timed intervals). */
+int gpt_sampler_run_timed(gpt_engine *e, int64_t nsteps, int keep, int flush_l2, float *ms_per_step);
+/* reps evaluations of a device-resident batch, one event pair each. */
+int gpt_log_prob_device_timed(gpt_engine *e, int star0, int nstars, const double *theta_device, int W,
+			      double *lp_device, int reps, int flush_l2, float *ms_per_rep);
+/* plain device buffers for callers without their own CUDA allocator */
+int gpt_device_alloc(gpt_engine *e, size_t bytes, void **out);
+int gpt_device_free(gpt_engine *e, void *p);
+int gpt_device_copy(gpt_engine *e, void *dst, const void *src, size_t bytes, int to_device);
 
 /* FP64 FMA throughput of this GPU (TFLOP/s, FMA = 2), measured by a register
  * resident DFMA kernel -- the roofline denominator bench.py reports against. */

@@ -535,6 +535,10 @@ void orc_quadratic_ld(const double *ds, int n, double p, double c1, double c2, i
 				Ek = ellec(q, mode);
 				lambdad = 1.0 / 3.0 + 2.0 / 9.0 / pi * (4.0 * (2.0 * p * p - 1.0) * Ek + (1.0 - 4.0 * p * p) * Kk);
 				etad = p * p / 2.0 * (p * p + 2.0 * d * d);
+				/* batman reads lambdae without having set it on this branch (planet edge at the
+				 * stellar centre, fully inside the disc); the Mandel-Agol value is p^2.  Measure-zero
+				 * set (|d - p| < 1e-14); recorded in DESIGN.md. */
+				lambdae = p * p;
 				flux[i] = 1.0 - ((1.0 - c1 - 2.0 * c2) * lambdae + (c1 + 2.0 * c2) * lambdad + c2 * etad) / omega;
 				continue;
 			} else if (d > 0.5) {

@@ -278,7 +278,7 @@ def test_multi_star_batch(engine):
         assert rel(lp[s], want) < RTOL
     # a sub-range of stars
     lp2 = engine.log_prob(theta[2:4], star=2, nstars=2)
-    assert np.array_equal(lp2, lp[2:4])
+    assert rel(lp2, lp[2:4]) < 1e-12     # chunk geometry depends on the batch size
 
 
 def test_sampler_matches_oracle_stream(engine, sim_lc, sim_config):
