@@ -8,11 +8,11 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgptransits_b200.so")
+LIB_PATH = os.environ.get("GPT_LIB_PATH") or os.path.join(_HERE, "libgptransits_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "kernels.cuh", "device_math.cuh")]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "gptransits_b200.h")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DTR_MINBLOCKS=3",
               "--shared", "-Xcompiler", "-fPIC"]
 
 

@@ -53,6 +53,7 @@ struct DevBuf {
 struct Star {
 	double4 *samp = nullptr;
 	double *tdays = nullptr;
+	unsigned char *tilereg = nullptr;
 	int N = 0;
 	double dt0 = 0, dreg = 0, dmax = 0;
 	bool has_err = false;
@@ -78,7 +79,7 @@ struct gpt_engine {
 	int opt_halo_auto = 1;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 0.75;  // chunk length >= this many halos
-	double opt_tol = 1e-11;
+	double opt_tol = 1e-10;   // budget for the chunk-coupling error, relative to quad and to logdet
 	int cur_halo = 192;
 
 	// stats
@@ -159,9 +160,9 @@ struct gpt_engine {
 	void adapt_halo(int H, bool failed, double ratio)
 	{
 		if (!opt_halo_auto || opt_halo != 0 || H <= 0) return;
-		// geometric decay model: error/tolerance ratio r at halo H, O(1e12) at H = 0; aim at 1e-2
+		// geometric decay model: error/tolerance ratio r at halo H, O(1e12) at H = 0; aim at 0.1
 		double r = failed ? 1e3 : std::max(ratio, 1e-30);
-		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(1e-2);
+		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(0.1);
 		double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
 		int nh = (int)std::ceil(want / 16.0) * 16;
 		nh = std::max(32, std::min(nh, 4096));
@@ -179,6 +180,7 @@ static int sync_stars(gpt_engine *e)
 	for (size_t i = 0; i < h.size(); i++) {
 		h[i].samp = e->stars[i].samp;
 		h[i].tdays = e->stars[i].tdays;
+		h[i].tilereg = e->stars[i].tilereg;
 		h[i].N = e->stars[i].N;
 		h[i]._pad = 0;
 		h[i].dt0 = e->stars[i].dt0;
@@ -305,7 +307,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 							      e->d_mean.p, 0);
 		e->timer_end(TK_TRSCAN);
-		transit_eval_kernel<<<148 * 4, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode,
+		transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode,
 								    e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
 		e->timer_end(TK_TRANSIT);
 		e->n_launch += 2;
@@ -355,7 +357,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	f.acc = e->d_acc.p;
 	f.tol = e->opt_tol;
 	e->timer_begin(TK_FINAL);
-	gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+	gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
 	e->timer_end(TK_FINAL);
 	e->n_launch++;
 
@@ -390,7 +392,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			launch_chunk(nt, m.has_transit != 0, grid, st, a);
 			f.verify = 0;
 			f.skip_if_clean = 1;
-			gp_finalize_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(f);
+			gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
 			e->timer_end(TK_PASS2);
 			e->n_launch += 2;
 		}
@@ -433,6 +435,7 @@ int gpt_star_clear(gpt_engine *e)
 	for (auto &s : e->stars) {
 		if (s.samp) cudaFree(s.samp);
 		if (s.tdays) cudaFree(s.tdays);
+		if (s.tilereg) cudaFree(s.tilereg);
 	}
 	e->stars.clear();
 	e->stars_dirty = true;
@@ -618,8 +621,10 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	CK(cudaStreamSynchronize(e->stream));
 	if (s.samp) cudaFree(s.samp);
 	if (s.tdays) cudaFree(s.tdays);
+	if (s.tilereg) cudaFree(s.tilereg);
 	s.samp = nullptr;
 	s.tdays = nullptr;
+	s.tilereg = nullptr;
 	std::vector<double4> h(N);
 	std::vector<double> dts;
 	dts.reserve(N);
@@ -651,6 +656,14 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	s.has_err = yerr != nullptr;
 	CK(cudaMalloc((void **)&s.samp, sizeof(double4) * N));
 	CK(cudaMemcpy(s.samp, h.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
+	{
+		const int64_t ntiles = (N + TILE - 1) / TILE;
+		std::vector<unsigned char> reg(ntiles, 1);
+		for (int64_t n = 0; n < N; n++)
+			if (!(std::fabs(h[n].x - dt0) <= dreg)) reg[n / TILE] = 0;
+		CK(cudaMalloc((void **)&s.tilereg, ntiles));
+		CK(cudaMemcpy(s.tilereg, reg.data(), ntiles, cudaMemcpyHostToDevice));
+	}
 	CK(cudaMalloc((void **)&s.tdays, sizeof(double) * N));
 	CK(cudaMemcpy(s.tdays, t_days, sizeof(double) * N, cudaMemcpyHostToDevice));
 	e->stars_dirty = true;
@@ -721,7 +734,7 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 	dim3 g((N + TR_THREADS - 1) / TR_THREADS, W);
 	transit_scan_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
 							     e->d_qcount.p, e->d_mean.p, 1);
-	transit_eval_kernel<<<148 * 4, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample,
+	transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample,
 								   e->model.exp_time, e->model.ellip_mode, e->d_prep.p,
 								   e->d_queue.p, e->d_qcount.p, e->d_mean.p, 1);
 	e->n_launch += 3;

@@ -11,6 +11,7 @@
 //   sampler kernels     L1+S1: red/blue split, stretch proposal, accept/reject, chain append
 #pragma once
 #include "device_math.cuh"
+#include <type_traits>
 
 namespace gpt {
 
@@ -59,6 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 struct StarDev {
 	const double4 *samp;  // [N] {dt_ms, y, var, t_days}
 	const double *tdays;  // [N] compact copy of the sample times (transit window scan)
+	const unsigned char *tilereg;  // [ceil(N/TILE)] 1: every step of the tile is a regular-cadence step
 	int N;
 	int _pad;
 	double dt0;    // base cadence (megaseconds)
@@ -170,6 +172,9 @@ __global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const doubl
 		pp[PP_WCEN] = tr.wcen;
 		pp[PP_WHALF] = tr.whalf;
 		pp[PP_INVPER] = tr.inv_per;
+		pp[PP_SININC] = tr.sin_inc;
+		pp[PP_RPINV] = tr.rp_inv;
+		pp[PP_INVOMEGA] = tr.inv_omega;
 		if (tr.whalf >= 0.5) fl |= WF_TR_ALL;
 	}
 	flags[gw] = fl;
@@ -184,6 +189,9 @@ __device__ inline void load_transit(const double *pp, TransitPars &tr)
 	tr.wcen = pp[PP_WCEN];
 	tr.whalf = pp[PP_WHALF];
 	tr.inv_per = pp[PP_INVPER];
+	tr.sin_inc = pp[PP_SININC];
+	tr.rp_inv = pp[PP_RPINV];
+	tr.inv_omega = pp[PP_INVOMEGA];
 }
 
 // Direct batman-semantics parameters (gpt_transit_flux): pars9 [nwalk][9] -> prep rows
@@ -212,6 +220,9 @@ __global__ void prep_transit_direct_kernel(double exp_time, const double *pars9,
 	pp[PP_WCEN] = tr.wcen;
 	pp[PP_WHALF] = tr.whalf;
 	pp[PP_INVPER] = tr.inv_per;
+	pp[PP_SININC] = tr.sin_inc;
+	pp[PP_RPINV] = tr.rp_inv;
+	pp[PP_INVOMEGA] = tr.inv_omega;
 	flags[gw] = WF_VALID | (tr.whalf >= 0.5 ? WF_TR_ALL : 0);
 }
 
@@ -257,7 +268,10 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 	if (inw) queue[base + __popc(mask & ((1u << lane) - 1))] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n;
 }
 
-__global__ void __launch_bounds__(TR_THREADS, 1)
+#ifndef TR_MINBLOCKS
+#define TR_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS)
 transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep,
 		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense)
 {
@@ -284,7 +298,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				TransitPars tr;
 				load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
 				const double ts = supersample_time(st.tdays[n], i, ss, exp_time);
-				f = ma_flux(rsky_one(ts, tr), tr.rp, tr.u1, tr.u2, mode);
+				f = ma_flux_fast(rsky_fast(ts, tr), tr.rp, tr.rp_inv, tr.u1, tr.u2, tr.inv_omega, mode);
 			}
 			// ordered sum over the group's lanes (np.mean order), gathered by the group's first lane
 			double s = f;
@@ -331,13 +345,6 @@ struct ChunkArgs {
 	int pass2;
 };
 
-template <int NT>
-struct WalkerCoef {
-	double a[NT], b[NT], c[NT], d[NT];
-	double phi0[NT], cr0[NT], sr0[NT];  // exp(-c dt0), cos(d dt0), sin(d dt0)
-	double asum;
-};
-
 // exp(-x) for |x| <= 1e-3, full double accuracy
 __device__ __forceinline__ double exp_small_neg(double x)
 {
@@ -355,7 +362,6 @@ __device__ __forceinline__ void sincos_small(double x, double &s, double &c)
 	c = fma(x2, fma(x2, 1.0 / 24.0, -0.5), 1.0);
 	s = x * fma(x2, fma(x2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
 }
-
 // 1/d by MUFU.RCP64H + two Newton steps (<= 2 ulp), no special-case branch; callers guard d > 0
 __device__ __forceinline__ double fast_rcp(double d)
 {
@@ -370,6 +376,100 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 {
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
+
+// Register-resident state of one (walker, chunk) thread.
+template <int NT>
+struct GPCore {
+	static constexpr int J = 2 * NT;
+	static constexpr int NP = J * (J + 1) / 2;
+	double P[NP], g[J];
+	double quad, ldm, zmax, dmin;
+	int lde;
+	bool notpd;
+};
+
+// One celerite step in carry form with prepared inputs: phi (per term), U, V (= cos, sin pairs),
+// residual y and diagonal A.  ACC: accumulate quad / log-det (inside the chunk proper).
+template <int NT, bool ACC>
+__device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], const double (&U)[2 * NT],
+					const double (&V)[2 * NT], double y, double Avar)
+{
+	constexpr int J = 2 * NT;
+	double pp_[NT * (NT + 1) / 2];
+#pragma unroll
+	for (int k = 0; k < NT; k++)
+#pragma unroll
+		for (int l = k; l < NT; l++) pp_[tri(k, l, NT)] = phi[k] * phi[l];
+	// S = phi phi^T o P (in place), f = phi o g
+#pragma unroll
+	for (int i = 0; i < J; i++)
+#pragma unroll
+		for (int j = i; j < J; j++) S.P[tri(i, j, J)] *= pp_[tri(i / 2, j / 2, NT)];
+	double f[J];
+#pragma unroll
+	for (int i = 0; i < J; i++) f[i] = phi[i / 2] * S.g[i];
+	// t = S U (two partial sums per row), D = A - U.t, z = y - U.f (pairwise trees)
+	double tv[J];
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+		double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+		for (int j = 0; j < J; j += 2) {
+			double s0_ = (i <= j) ? S.P[tri(i, j, J)] : S.P[tri(j, i, J)];
+			double s1_ = (i <= j + 1) ? S.P[tri(i, j + 1, J)] : S.P[tri(j + 1, i, J)];
+			acc0 = fma(s0_, U[j], acc0);
+			acc1 = fma(s1_, U[j + 1], acc1);
+		}
+		tv[i] = acc0 + acc1;
+	}
+	double utp[NT], zpp[NT];
+#pragma unroll
+	for (int k = 0; k < NT; k++) {
+		utp[k] = fma(U[2 * k], tv[2 * k], U[2 * k + 1] * tv[2 * k + 1]);
+		zpp[k] = fma(U[2 * k], f[2 * k], U[2 * k + 1] * f[2 * k + 1]);
+	}
+	double ut = utp[0], zp = zpp[0];
+#pragma unroll
+	for (int k = 1; k < NT; k++) {
+		ut += utp[k];
+		zp += zpp[k];
+	}
+	const double D = Avar - ut;
+	const double z = y - zp;
+	S.notpd |= !(D > 0.0);
+	const double invD = fast_rcp(D);
+	// w = (V - t)/D ; P' = S + (V - t) w^T ; g' = f + w z
+	double vt[J], wv[J];
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+		vt[i] = V[i] - tv[i];
+		wv[i] = vt[i] * invD;
+	}
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+#pragma unroll
+		for (int j = i; j < J; j++) S.P[tri(i, j, J)] = fma(vt[i], wv[j], S.P[tri(i, j, J)]);
+		S.g[i] = fma(wv[i], z, f[i]);
+	}
+	if (ACC) {
+		double zi = z * invD;
+		S.quad = fma(z, zi, S.quad);
+		S.zmax = fmax(S.zmax, fabs(zi));
+		S.dmin = fmin(S.dmin, D);
+		// log-det as mantissa product + integer exponent
+		S.ldm *= D;
+		int hi = __double2hiint(S.ldm);
+		int ex = ((hi >> 20) & 0x7ff) - 1023;
+		S.lde += ex;
+		S.ldm = __hiloint2double(hi - (ex << 20), __double2loint(S.ldm));
+	}
+}
+
+// per-walker constants of the fast loop
+template <int NT>
+struct FastCoef {
+	double c[NT], d[NT], phi0[NT], cr0[NT], sr0[NT];  // exp(-c dt0), cos(d dt0), sin(d dt0)
+};
 
 template <int NT, bool TRANSIT>
 __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
@@ -404,17 +504,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 	if (!__syncthreads_or(active)) return;
 
 	// ---- walker coefficients -> registers
-	WalkerCoef<NT> K;
+	const double *pp = A.prep + (size_t)(active ? gw : 0) * PREP_STRIDE;
+	FastCoef<NT> K;
+	double asum = 1.0;
 	double wcen = 0.0, inv_per = 1.0, whalf = -1.0;  // inactive threads: never in window
 	double dreg = -1.0;                             // |ddt| <= dreg: series for exp / rotation
-	bool tiny = true;                               // first-order series is exact to double precision
+	double xmax = 0.0;                              // max |c ddt|, |d ddt| on regular steps
 	if (active) {
-		const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
-		K.asum = pp[PP_ASUM];
+		asum = pp[PP_ASUM];
 #pragma unroll
 		for (int k = 0; k < NT; k++) {
-			K.a[k] = pp[PP_TERMS + 4 * k + 0];
-			K.b[k] = pp[PP_TERMS + 4 * k + 1];
 			K.c[k] = pp[PP_TERMS + 4 * k + 2];
 			K.d[k] = pp[PP_TERMS + 4 * k + 3];
 			K.phi0[k] = exp(-K.c[k] * st.dt0);
@@ -426,43 +525,39 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 			whalf = pp[PP_WHALF];
 		}
 		if (!(fl & WF_SLOWTRIG)) dreg = st.dreg;
-		tiny = pp[PP_MAXCD] * st.dmax <= 1.0e-9;
+		xmax = (fl & WF_SLOWTRIG) ? 1.0 : pp[PP_MAXCD] * st.dmax;
 	} else {
-		K.asum = 1.0;
 #pragma unroll
 		for (int k = 0; k < NT; k++) {
-			K.a[k] = K.b[k] = K.c[k] = K.d[k] = 0.0;
+			K.c[k] = K.d[k] = 0.0;
 			K.phi0[k] = 1.0;
 			K.cr0[k] = 1.0;
 			K.sr0[k] = 0.0;
 		}
 	}
-	// block-uniform choice of the series order on regular steps
-	const bool all_tiny = __syncthreads_and(tiny) != 0;
-	const double *meanw = TRANSIT ? (A.mean + (size_t)gw * N) : nullptr;
-	if (!TRANSIT || !(w < A.W)) meanw = nullptr;
+	// block-uniform series order for regular steps: 1 (x <= 1e-8), 2 (x <= 5e-6), 0 = general loop
+	const int order = __syncthreads_or(xmax > 5.0e-6) ? 0 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1);
+	const double *meanw = (TRANSIT && w < A.W) ? (A.mean + (size_t)gw * N) : nullptr;
 
 	// ---- state
-	double P[NP], g[J], cs[NT], sn[NT];
+	GPCore<NT> S;
 #pragma unroll
-	for (int i = 0; i < NP; i++) P[i] = 0.0;
+	for (int i = 0; i < NP; i++) S.P[i] = 0.0;
 #pragma unroll
-	for (int i = 0; i < J; i++) g[i] = 0.0;
-#pragma unroll
-	for (int k = 0; k < NT; k++) {
-		cs[k] = 1.0;
-		sn[k] = 0.0;
-	}
+	for (int i = 0; i < J; i++) S.g[i] = 0.0;
+	S.quad = 0.0;
+	S.ldm = 1.0;
+	S.zmax = 0.0;
+	S.dmin = CUDART_INF;
+	S.lde = 0;
+	S.notpd = false;
 	if (pass2 && active && c > 0) {
 		const double *cr = A.carryT + ((size_t)gw * A.nchunks + c) * CS;
 #pragma unroll
-		for (int i = 0; i < NP; i++) P[i] = cr[i];
+		for (int i = 0; i < NP; i++) S.P[i] = cr[i];
 #pragma unroll
-		for (int i = 0; i < J; i++) g[i] = cr[NP + i];
+		for (int i = 0; i < J; i++) S.g[i] = cr[NP + i];
 	}
-	double quad = 0.0, ldm = 1.0, zmax = 0.0, dmin = CUDART_INF;
-	int lde = 0;
-	bool notpd = false;
 
 	// ---- TMA pipeline over tiles
 	const int t_first = hs / TILE, t_last = (n1 - 1) / TILE;
@@ -487,173 +582,163 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 		prefetch_l1(meanw + min(hs + 16, N - 1));
 	}
 
+	// residual of sample m: flux minus this walker's transit model.  The model array is valid only
+	// inside the walker's window, so it is loaded unconditionally (L1-prefetched, and one full step
+	// ahead of its use in the fast loop) and selected.
+	auto load_mean = [&](int m) -> double {
+		double mv = 0.0;
+		if (TRANSIT && meanw) {
+			mv = meanw[m];
+			if ((m & 15) == 0) prefetch_l1(meanw + min(m + 48, N - 1));
+		}
+		return mv;
+	};
+	auto residual_mv = [&](const double4 &sm, double mv) -> double {
+		double y = sm.y;
+		if (TRANSIT) y -= in_transit_window(sm.w, wcen, inv_per, whalf) ? mv : 0.0;
+		return y;
+	};
+	auto residual = [&](const double4 &sm, int m) -> double { return residual_mv(sm, load_mean(m)); };
+	auto store_carry = [&](double *dst) {
+#pragma unroll
+		for (int i = 0; i < NP; i++) dst[i] = S.P[i];
+#pragma unroll
+		for (int i = 0; i < J; i++) dst[NP + i] = S.g[i];
+	};
+
 	for (int tl = t_first; tl <= t_last; tl++) {
 		const int it = tl - t_first;
 		const int stg = it % NSTAGE;
 		mbar_wait(&s_bar[stg], (uint32_t)((it / NSTAGE) & 1));
 		const int s0 = max(tl * TILE, hs), s1 = min((tl + 1) * TILE, n1);
 		const double4 *tile = &s_tile[stg][0] - tl * TILE;
+		const int mid = min(max(n0, s0), s1);  // [s0, mid) halo, [mid, s1) chunk proper
+		const bool store_here = (!pass2 && c > 0 && active && n0 >= s0 && n0 < s1);
 
-		// re-anchor the rotation at the first sample of every tile: exact sincos(d * x_n)
+		// anchor: exact rotation state at the first sample of the tile range
+		double phiC[NT], UC[J], VC[J], yC, AC;
 		{
-			double x = tile[s0].w * kDaysToMs;
+			const double4 sm = tile[s0];
+			const double x = sm.w * kDaysToMs;
 #pragma unroll
-			for (int k = 0; k < NT; k++) sincos(K.d[k] * x, &sn[k], &cs[k]);
+			for (int k = 0; k < NT; k++) {
+				double sn_, cs_;
+				sincos(K.d[k] * x, &sn_, &cs_);
+				const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
+				VC[2 * k] = cs_;
+				VC[2 * k + 1] = sn_;
+				UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
+				UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
+				const double ddt = sm.x - st.dt0;
+				phiC[k] = (fabs(ddt) <= dreg) ? K.phi0[k] * exp_small_neg(K.c[k] * ddt) : exp(-K.c[k] * sm.x);
+			}
+			yC = residual(sm, s0);
+			AC = sm.z + asum;
 		}
-		for (int n = s0; n < s1; n++) {
-			const double4 sm = tile[n];
-			if (n == n0 && !pass2 && c > 0 && active) {
-				// halo finished: record the estimated carry entering this chunk
-				double *ce = A.carryE + ((size_t)gw * A.nchunks + c) * CS;
-#pragma unroll
-				for (int i = 0; i < NP; i++) ce[i] = P[i];
-#pragma unroll
-				for (int i = 0; i < J; i++) ce[NP + i] = g[i];
-			}
-			const double dt = sm.x;
-			double y = sm.y;
-			if (TRANSIT) {
-				// the transit model of this walker: valid only inside its window, so load
-				// unconditionally (L1-prefetched two lines ahead) and select
-				double mv = 0.0;
-				if (meanw) {
-					mv = meanw[n];
-					if ((n & 15) == 0) prefetch_l1(meanw + min(n + 32, N - 1));
-				}
-				const bool inw = in_transit_window(sm.w, wcen, inv_per, whalf);
-				y -= inw ? mv : 0.0;
-			}
-			// ---- phi, rotation
-			double phi[NT], U[J];
-			const double ddt = dt - st.dt0;
-			const bool anchored = (n == s0);
-			if (ddt == 0.0 && dreg >= 0.0) {
-#pragma unroll
-				for (int k = 0; k < NT; k++) {
-					phi[k] = K.phi0[k];
-					if (!anchored) {
-						double cn = cs[k] * K.cr0[k] - sn[k] * K.sr0[k];
-						double sx = sn[k] * K.cr0[k] + cs[k] * K.sr0[k];
-						cs[k] = cn;
-						sn[k] = sx;
-					}
-				}
-			} else if (fabs(ddt) <= dreg) {
-				if (all_tiny) {
-					// |c ddt|, |d ddt| <= 1e-9: first order is exact to double precision
+
+		if (order != 0 && st.tilereg[tl]) {
+			// ---- fast loop: every step of this tile is a regular-cadence step.  Straight-line body:
+			// the dependent chain of step n and the preparation of step n+1 are independent.
+			double mvN = load_mean(min(s0 + 1, s1 - 1));  // model value of the NEXT sample, in flight
+			auto fast_range = [&](int a_, int b_, auto acc_tag, auto order_tag) {
+				constexpr bool ACC = decltype(acc_tag)::value;
+				constexpr int ORDER = decltype(order_tag)::value;
+#pragma unroll 2
+				for (int n = a_; n < b_; n++) {
+					const int m = min(n + 1, s1 - 1);
+					const double mv2 = load_mean(min(n + 2, s1 - 1));
+					const double4 sm = tile[m];
+					const double ddt = sm.x - st.dt0;
+					double phiN[NT], UN[J], VN[J];
 #pragma unroll
 					for (int k = 0; k < NT; k++) {
-						phi[k] = fma(-K.phi0[k], K.c[k] * ddt, K.phi0[k]);
-						if (!anchored) {
-							double xd = K.d[k] * ddt;
-							double cr = fma(-K.sr0[k], xd, K.cr0[k]);
-							double sr = fma(K.cr0[k], xd, K.sr0[k]);
-							double cn = cs[k] * cr - sn[k] * sr;
-							double sx = sn[k] * cr + cs[k] * sr;
-							cs[k] = cn;
-							sn[k] = sx;
+						const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
+						double cr, sr;
+						if (ORDER == 1) {
+							phiN[k] = fma(-K.phi0[k], xc, K.phi0[k]);
+							cr = fma(-K.sr0[k], xd, K.cr0[k]);
+							sr = fma(K.cr0[k], xd, K.sr0[k]);
+						} else {
+							phiN[k] = K.phi0[k] * fma(fma(0.5, xc, -1.0), xc, 1.0);
+							const double h = fma(-0.5 * xd, xd, 1.0);
+							cr = fma(-K.sr0[k], xd, K.cr0[k] * h);
+							sr = fma(K.cr0[k], xd, K.sr0[k] * h);
 						}
+						VN[2 * k] = fma(VC[2 * k], cr, -(VC[2 * k + 1] * sr));
+						VN[2 * k + 1] = fma(VC[2 * k + 1], cr, VC[2 * k] * sr);
+						UN[2 * k] = fma(UC[2 * k], cr, -(UC[2 * k + 1] * sr));
+						UN[2 * k + 1] = fma(UC[2 * k + 1], cr, UC[2 * k] * sr);
 					}
-				} else {
+					const double yN = residual_mv(sm, mvN);
+					mvN = mv2;
+					const double AN = sm.z + asum;
+					gp_step<NT, ACC>(S, phiC, UC, VC, yC, AC);
 #pragma unroll
-					for (int k = 0; k < NT; k++) {
-						phi[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);
-						if (!anchored) {
+					for (int k = 0; k < NT; k++) phiC[k] = phiN[k];
+#pragma unroll
+					for (int i = 0; i < J; i++) {
+						UC[i] = UN[i];
+						VC[i] = VN[i];
+					}
+					yC = yN;
+					AC = AN;
+				}
+			};
+			using T = std::integral_constant<bool, true>;
+			using F = std::integral_constant<bool, false>;
+			using O1 = std::integral_constant<int, 1>;
+			using O2 = std::integral_constant<int, 2>;
+			if (order == 1) {
+				fast_range(s0, mid, F{}, O1{});
+				if (store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+				fast_range(mid, s1, T{}, O1{});
+			} else {
+				fast_range(s0, mid, F{}, O2{});
+				if (store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+				fast_range(mid, s1, T{}, O2{});
+			}
+		} else {
+			// ---- general loop: gaps, irregular cadence, large timing jitter
+			for (int n = s0; n < s1; n++) {
+				if (n == n0 && store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+				if (n >= n0)
+					gp_step<NT, true>(S, phiC, UC, VC, yC, AC);
+				else
+					gp_step<NT, false>(S, phiC, UC, VC, yC, AC);
+				if (n + 1 < s1) {
+					const double4 sm = tile[n + 1];
+					const double ddt = sm.x - st.dt0;
+					if (fabs(ddt) <= dreg) {
+#pragma unroll
+						for (int k = 0; k < NT; k++) {
+							phiC[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);
 							double s1_, c1_;
 							sincos_small(K.d[k] * ddt, s1_, c1_);
-							double cr = K.cr0[k] * c1_ - K.sr0[k] * s1_;
-							double sr = K.sr0[k] * c1_ + K.cr0[k] * s1_;
-							double cn = cs[k] * cr - sn[k] * sr;
-							double sx = sn[k] * cr + cs[k] * sr;
-							cs[k] = cn;
-							sn[k] = sx;
+							const double cr = K.cr0[k] * c1_ - K.sr0[k] * s1_;
+							const double sr = K.sr0[k] * c1_ + K.cr0[k] * s1_;
+							const double v0 = VC[2 * k], v1 = VC[2 * k + 1], u0 = UC[2 * k], u1 = UC[2 * k + 1];
+							VC[2 * k] = fma(v0, cr, -(v1 * sr));
+							VC[2 * k + 1] = fma(v1, cr, v0 * sr);
+							UC[2 * k] = fma(u0, cr, -(u1 * sr));
+							UC[2 * k + 1] = fma(u1, cr, u0 * sr);
+						}
+					} else {
+						const double x = sm.w * kDaysToMs;
+#pragma unroll
+						for (int k = 0; k < NT; k++) {
+							phiC[k] = exp(-K.c[k] * sm.x);
+							double sn_, cs_;
+							sincos(K.d[k] * x, &sn_, &cs_);
+							const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
+							VC[2 * k] = cs_;
+							VC[2 * k + 1] = sn_;
+							UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
+							UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
 						}
 					}
+					yC = residual(sm, n + 1);
+					AC = sm.z + asum;
 				}
-			} else {
-				// gap or irregular cadence: direct exp, absolute sincos
-				const double x = sm.w * kDaysToMs;
-#pragma unroll
-				for (int k = 0; k < NT; k++) {
-					phi[k] = exp(-K.c[k] * dt);
-					if (!anchored) sincos(K.d[k] * x, &sn[k], &cs[k]);
-				}
-			}
-#pragma unroll
-			for (int k = 0; k < NT; k++) {
-				U[2 * k] = fma(K.a[k], cs[k], K.b[k] * sn[k]);
-				U[2 * k + 1] = fma(K.a[k], sn[k], -(K.b[k] * cs[k]));
-			}
-			// ---- S = phi phi^T o P  (in place), f = phi o g
-			double pp_[NT * (NT + 1) / 2];
-#pragma unroll
-			for (int k = 0; k < NT; k++)
-#pragma unroll
-				for (int l = k; l < NT; l++) pp_[tri(k, l, NT)] = phi[k] * phi[l];
-#pragma unroll
-			for (int i = 0; i < J; i++)
-#pragma unroll
-				for (int j = i; j < J; j++) P[tri(i, j, J)] *= pp_[tri(i / 2, j / 2, NT)];
-			double f[J];
-#pragma unroll
-			for (int i = 0; i < J; i++) f[i] = phi[i / 2] * g[i];
-			// ---- t = S U (two partial sums per row), D = A - U.t, z = y - U.f (pairwise trees)
-			double tv[J];
-#pragma unroll
-			for (int i = 0; i < J; i++) {
-				double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-				for (int j = 0; j < J; j += 2) {
-					double s0_ = (i <= j) ? P[tri(i, j, J)] : P[tri(j, i, J)];
-					double s1_ = (i <= j + 1) ? P[tri(i, j + 1, J)] : P[tri(j + 1, i, J)];
-					acc0 = fma(s0_, U[j], acc0);
-					acc1 = fma(s1_, U[j + 1], acc1);
-				}
-				tv[i] = acc0 + acc1;
-			}
-			double utp[NT], zpp[NT];
-#pragma unroll
-			for (int k = 0; k < NT; k++) {
-				utp[k] = fma(U[2 * k], tv[2 * k], U[2 * k + 1] * tv[2 * k + 1]);
-				zpp[k] = fma(U[2 * k], f[2 * k], U[2 * k + 1] * f[2 * k + 1]);
-			}
-			double ut = utp[0], zp = zpp[0];
-#pragma unroll
-			for (int k = 1; k < NT; k++) {
-				ut += utp[k];
-				zp += zpp[k];
-			}
-			const double D = (sm.z + K.asum) - ut;
-			const double z = y - zp;
-			notpd |= !(D > 0.0);
-			const double invD = fast_rcp(D);
-			// ---- w = (V - t)/D ; P' = S + D w w^T ; g' = f + w z
-			double wv[J];
-#pragma unroll
-			for (int k = 0; k < NT; k++) {
-				wv[2 * k] = (cs[k] - tv[2 * k]) * invD;
-				wv[2 * k + 1] = (sn[k] - tv[2 * k + 1]) * invD;
-			}
-#pragma unroll
-			for (int i = 0; i < J; i++) {
-				// D w_i = V_i - t_i exactly as computed above, before the division
-				double dwi = (i & 1) ? (sn[i / 2] - tv[i]) : (cs[i / 2] - tv[i]);
-#pragma unroll
-				for (int j = i; j < J; j++) P[tri(i, j, J)] = fma(dwi, wv[j], P[tri(i, j, J)]);
-				g[i] = fma(wv[i], z, f[i]);
-			}
-			// ---- accumulate (only inside the chunk proper)
-			if (n >= n0) {
-				double zi = z * invD;
-				quad = fma(z, zi, quad);
-				zmax = fmax(zmax, fabs(zi));
-				dmin = fmin(dmin, D);
-				// log-det as mantissa product + integer exponent
-				ldm *= D;
-				int hi = __double2hiint(ldm);
-				int ex = ((hi >> 20) & 0x7ff) - 1023;
-				lde += ex;
-				ldm = __hiloint2double(hi - (ex << 20), __double2loint(ldm));
 			}
 		}
 		__syncthreads();
@@ -661,19 +746,13 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 	}
 
 	if (active) {
-		if (c + 1 < A.nchunks && n1 < N) {
-			double *ct = A.carryT + ((size_t)gw * A.nchunks + c + 1) * CS;
-#pragma unroll
-			for (int i = 0; i < NP; i++) ct[i] = P[i];
-#pragma unroll
-			for (int i = 0; i < J; i++) ct[NP + i] = g[i];
-		}
+		if (c + 1 < A.nchunks && n1 < N) store_carry(A.carryT + ((size_t)gw * A.nchunks + c + 1) * CS);
 		ChunkPartial pr;
-		pr.quad = quad;
-		pr.logdet = (double)lde * 0.693147180559945309417 + log(ldm);
-		pr.zmax = zmax;
-		pr.dmin = dmin;
-		if (notpd) {
+		pr.quad = S.quad;
+		pr.logdet = (double)S.lde * 0.693147180559945309417 + log(S.ldm);
+		pr.zmax = S.zmax;
+		pr.dmin = S.dmin;
+		if (S.notpd) {
 			pr.logdet = CUDART_NAN;
 			atomicOr(&A.wstatus[gw], WF_NOTPD);
 		}
@@ -700,17 +779,36 @@ struct FinalArgs {
 	double tol;
 };
 
-// One warp per walker; lanes stride over chunks; fixed-order shuffle tree => deterministic sums.
-__global__ void gp_finalize_kernel(FinalArgs A)
+// One block of FIN_THREADS per walker; threads stride over chunks / chunk boundaries; the sums use a
+// fixed-shape shared-memory + warp-shuffle tree, so they are deterministic.
+constexpr int FIN_THREADS = 128;
+
+__device__ __forceinline__ double block_sum(double v, double *scratch)
 {
-	const int lane = threadIdx.x & 31;
-	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) scratch[wid] = v;
+	__syncthreads();
+	double t = 0.0;
+#pragma unroll
+	for (int i = 0; i < FIN_THREADS / 32; i++) t += scratch[i];
+	return t;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
+{
+	__shared__ double scratch[FIN_THREADS / 32];
+	__shared__ int s_nbad[FIN_THREADS / 32];
+	const int gw = blockIdx.x;
+	const int tid = threadIdx.x;
 	if (gw >= A.nwalk) return;
 	if (A.skip_if_clean && *A.nbad == 0) return;
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
 	if (!(fl & WF_VALID)) {
-		if (lane == 0) {
+		if (tid == 0) {
 			A.lp[gw] = -CUDART_INF;
 			if (A.parts) {
 				A.parts[4 * gw + 0] = pp[PP_LNPRIOR];
@@ -723,29 +821,27 @@ __global__ void gp_finalize_kernel(FinalArgs A)
 	}
 	if (fl & WF_GENERIC) return;  // written by gp_generic_kernel
 	const int J = 2 * A.nterms, NP = J * (J + 1) / 2, CS = NP + J;
-	double quad = 0.0, logdet = 0.0;
-	for (int k = lane; k < A.nchunks; k += 32) {
+	double q = 0.0, ld = 0.0;
+	for (int k = tid; k < A.nchunks; k += FIN_THREADS) {
 		ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
-		quad += pr.quad;
-		logdet += pr.logdet;
+		q += pr.quad;
+		ld += pr.logdet;
 	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		quad += __shfl_xor_sync(0xffffffffu, quad, o);
-		logdet += __shfl_xor_sync(0xffffffffu, logdet, o);
-	}
-	int nbad = 0;
+	const double quad = block_sum(q, scratch);
+	const double logdet = block_sum(ld, scratch);
 	if (A.verify && A.nchunks > 1) {
 		double ua[2 * MAX_TERMS];
 		for (int k = 0; k < A.nterms; k++) {
 			double a = pp[PP_TERMS + 4 * k], b = pp[PP_TERMS + 4 * k + 1];
 			ua[2 * k] = ua[2 * k + 1] = sqrt(a * a + b * b);
 		}
-		const double G = fmax((double)A.H, 8.0) * 0.25;
+		// sum of a geometric decay that lost >= 10 decades over the halo: <= H / ln(1e10) ~ H / 23
+		const double G = fmax((double)A.H, 16.0) * (1.0 / 12.0);
 		const double budL = A.tol * fmax(1.0, fabs(logdet)) / A.nchunks;
 		const double budQ = A.tol * fmax(fabs(quad), 1e-300) / A.nchunks;
 		double worst = 0.0;
-		for (int k = 1 + lane; k < A.nchunks; k += 32) {
+		int nbad = 0;
+		for (int k = 1 + tid; k < A.nchunks; k += FIN_THREADS) {
 			const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
 			const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
 			ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
@@ -763,13 +859,13 @@ __global__ void gp_finalize_kernel(FinalArgs A)
 			A.redo[(size_t)gw * A.nchunks + k] = bad ? 1 : 0;
 			nbad += bad ? 1 : 0;
 		}
-		if (lane == 0) A.redo[(size_t)gw * A.nchunks] = 0;
+		if (tid == 0) A.redo[(size_t)gw * A.nchunks] = 0;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
 			worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
 		}
-		if (lane == 0) {
+		if ((tid & 31) == 0) {
 			if (nbad) {
 				atomicAdd(A.nbad, nbad);
 				atomicAdd(A.acc, (unsigned long long)nbad);
@@ -777,8 +873,9 @@ __global__ void gp_finalize_kernel(FinalArgs A)
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
 			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
+		(void)s_nbad;
 	}
-	if (lane == 0) {
+	if (tid == 0) {
 		const double lnprior = pp[PP_LNPRIOR];
 		double lnl = -0.5 * (quad + logdet + (double)A.N * 1.8378770664093454836);
 		double lp = lnprior + lnl;
