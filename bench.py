@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="size of the bounded CPU sample")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--batch-walkers", type=int, default=2048,
+                    help="size of the extra resident log_prob batch (0 = skip)")
     return ap.parse_args()
 
 
@@ -117,7 +119,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -216,7 +218,19 @@ def run_ours(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout at the first collective: keep stdout for the
+        # single JSON line by pointing fd 1 at stderr while the communicator is brought up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from gptransits_b200 import Engine
 
     work = build_workload(args.workload, rank, args)
@@ -257,7 +271,7 @@ def run_ours(args):
     ms = eng.sampler_run_timed(args.steps, keep=True, flush_l2=flush)
     launches = int(eng.stat("launches") - l0)
     barrier()
-    clk = clocks.stop()
+    geom = {k: eng.stat(k) for k in ("chunks", "chunk_len", "halo")}
     total_ms = max_over_ranks(float(ms.sum()))
     evals_per_step = W * nstars * world
     value = evals_per_step * args.steps / (total_ms * 1e-3)
@@ -268,6 +282,7 @@ def run_ours(args):
     ms2 = eng.sampler_run_timed(args.steps, keep=True, flush_l2=flush)
     kern = {k: (eng.stat("ms_" + k), eng.stat("n_" + k)) for k in ("prep", "transit", "chunk", "final", "pass2")}
     eng.set_option("time_kernels", 0)
+    clk = clocks.stop()
     _, _, nacc = eng.sampler_state()
     eng.sampler_end()
     chunk_ms, chunk_n = kern["chunk"]
@@ -303,7 +318,28 @@ def run_ours(args):
     for _ in range(reps):
         eng.log_prob(th, nstars=nstars)
     lp_rate = th.shape[0] * reps / (time.perf_counter() - t0)
-    stats = {k: eng.stat(k) for k in ("chunks", "chunk_len", "halo", "pass2_chunks", "verify_ratio")}
+    stats = {k: eng.stat(k) for k in ("pass2_chunks", "verify_ratio")}
+    stats.update(geom)
+
+    # ---- large resident batch of the same star: long chunks, little halo overhead (kernel efficiency view)
+    batched = None
+    if world == 1 and args.batch_walkers > 0:
+        WB = args.batch_walkers
+        np.random.seed(args.seed + 1000)
+        thb = np.hstack([gp.sample_prior(WB), tr.sample_prior(WB)])
+        eng.log_prob(thb[:WB])
+        eng.log_prob(thb[:WB])
+        eng.set_option("reset_timers", 1)
+        eng.set_option("time_kernels", 1)
+        _, msb = eng.log_prob_resident_timed(thb, 5, flush_l2=flush)
+        kb = {k: eng.stat("ms_" + k) / max(1.0, eng.stat("n_" + k)) for k in ("transit", "chunk", "final", "pass2")}
+        eng.set_option("time_kernels", 0)
+        fb = F_GP[J] * N * WB
+        batched = {"walkers": WB, "evals_per_s": WB / (float(np.median(msb)) * 1e-3), "ms": float(np.median(msb)),
+                   "kernel_ms": kb, "chunk_tflops": fb / (kb["chunk"] * 1e-3) / 1e12,
+                   "chunk_frac": fb / (kb["chunk"] * 1e-3) / 1e12 / peak_tf,
+                   "whole_eval_frac": (F_GP[J] + F_TR) * N * WB / (float(np.median(msb)) * 1e-3) / 1e12 / peak_tf,
+                   "chunks": eng.stat("chunks"), "chunk_len": eng.stat("chunk_len"), "halo": eng.stat("halo")}
 
     cpu = None
     if rank == 0 and world == 1:
@@ -344,6 +380,8 @@ def run_ours(args):
                          "pass2_chunks": stats["pass2_chunks"], "verify_ratio": stats["verify_ratio"]},
             "clocks": clk,
         }
+        if batched:
+            out["batched_log_prob"] = batched
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))

@@ -362,79 +362,102 @@ __device__ inline double ellpic_fast(double n, double k, double tol)
 	return 0.0;
 }
 
-// rp_inv = 1/p, inv_omega = 1/(1 - c1/3 - c2/6): per-walker constants
+// rp_inv = 1/p, inv_omega = 1/(1 - c1/3 - c2/6): per-walker constants.
+// Structure: the case analysis only selects coefficients (q^2, n, prefactor, cK, cE, cP, lambda_e,
+// eta_d); K, E, Pi and the combination lambda_d = pref (cK K + cE E - cP Pi) run once, converged,
+// for every in-transit lane of the warp.
 __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double c1, double c2, double inv_omega, int mode)
 {
-	const double pi = kPi, inv_pi = 0.31830988618379067154;
+	const double inv_pi = 0.31830988618379067154;
 	const double tol = 1.0e-14;
-	double lambdad = 0.0, etad = 0.0, lambdae = 0.0, kap0 = 0.0, kap1 = 0.0;
 	d = fabs(d);
 	if (fabs(p - d) < tol) d = p;
 	if (fabs(p - 1.0 - d) < tol) d = p - 1.0;
 	if (fabs(1.0 - p - d) < tol) d = 1.0 - p;
 	if (d < tol) d = 0.0;
-	if (d >= 1.0 + p) return 1.0;
 	const double p2 = p * p, d2 = d * d;
 	const double x1 = (p - d) * (p - d), x2 = (p + d) * (p + d), x3 = p2 - d2;
 	const double w1 = 1.0 - c1 - 2.0 * c2, w2 = c1 + 2.0 * c2;
-	if (p >= 1.0 && d <= p - 1.0) return 1.0 - (w1 + w2 * (2.0 / 3.0) + c2 * 0.5) * inv_omega;
-	const double ptol = 1.0e-8;
-	const double pitol = mode == 0 ? ptol : 1.0e-10;
-	if (d >= fabs(1.0 - p) && d <= 1.0 + p) {
-		const double rd = rcp_nr(d);
-		kap1 = acos(fmin((1.0 - p2 + d2) * 0.5 * rd, 1.0));
-		kap0 = acos(fmin((p2 + d2 - 1.0) * 0.5 * rp_inv * rd, 1.0));
-		const double tt = 1.0 + d2 - p2;
-		lambdae = (p2 * kap0 + kap1 - 0.50 * sqrt(fmax(4.0 * d2 - tt * tt, 0.0))) * inv_pi;
-	}
-	if (d == p) {
-		double Kk, Ek;
-		if (d < 0.5) {
-			ellke_fast(2.0 * p, mode, Kk, Ek);
-			lambdad = 1.0 / 3.0 + (2.0 / 9.0) * inv_pi * (4.0 * (2.0 * p2 - 1.0) * Ek + (1.0 - 4.0 * p2) * Kk);
+	const double pitol = mode == 0 ? 1.0e-8 : 1.0e-10;
+
+	double lambdad = 0.0, etad = 0.0, lambdae = 0.0, kap0 = 0.0, kap1 = 0.0;
+	double q2 = 0.0, nn = 0.0, pref = 0.0, cK = 0.0, cE = 0.0, cP = 0.0, add = 0.0;
+	bool elliptic = false, done = false;
+	double result = 1.0;
+
+	if (d >= 1.0 + p) {
+		done = true;  // unocculted
+	} else if (p >= 1.0 && d <= p - 1.0) {
+		result = 1.0 - (w1 + w2 * (2.0 / 3.0) + c2 * 0.5) * inv_omega;  // fully occulted
+		done = true;
+	} else {
+		if (d >= fabs(1.0 - p) && d <= 1.0 + p) {
+			// planet crosses the limb: uniform-source term from the two arcs
+			const double rd = rcp_nr(d);
+			kap1 = acos(fmin((1.0 - p2 + d2) * 0.5 * rd, 1.0));
+			kap0 = acos(fmin((p2 + d2 - 1.0) * 0.5 * rp_inv * rd, 1.0));
+			const double tt = 1.0 + d2 - p2;
+			lambdae = (p2 * kap0 + kap1 - 0.50 * sqrt(fmax(4.0 * d2 - tt * tt, 0.0))) * inv_pi;
+		}
+		if (d == p) {
+			// planet edge at the stellar centre (measure-zero set): closed forms in K, E only
+			double Kk, Ek;
+			if (d < 0.5) {
+				ellke_fast(2.0 * p, mode, Kk, Ek);
+				lambdad = 1.0 / 3.0 + (2.0 / 9.0) * inv_pi * (4.0 * (2.0 * p2 - 1.0) * Ek + (1.0 - 4.0 * p2) * Kk);
+				etad = p2 * 0.5 * (p2 + 2.0 * d2);
+				lambdae = p2;
+			} else if (d > 0.5) {
+				ellke_fast(0.5 * rp_inv, mode, Kk, Ek);
+				lambdad = 1.0 / 3.0 + (16.0 / 9.0) * p * inv_pi * (2.0 * p2 - 1.0) * Ek -
+					  (32.0 * p2 * p2 - 20.0 * p2 + 3.0) * (1.0 / 9.0) * inv_pi * rp_inv * Kk;
+				etad = 0.5 * inv_pi * (kap1 + p2 * (p2 + 2.0 * d2) * kap0 - (1.0 + 5.0 * p2 + d2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
+			} else {
+				lambdad = 1.0 / 3.0 - 4.0 * inv_pi / 9.0;
+				etad = 3.0 / 32.0;
+			}
+		} else if ((d > 0.5 + fabs(p - 0.5) && d < 1.0 + p) || (p > 0.5 && d > fabs(1.0 - p) && d < p)) {
+			// ingress / egress
+			const double rdp = rcp_nr(d * p);
+			q2 = (1.0 - x1) * 0.25 * rdp;
+			const double rx1 = rcp_nr(x1);
+			nn = rx1 - 1.0;
+			pref = (1.0 / 9.0) * inv_pi * sqrt(rdp);
+			cK = (1.0 - x2) * (2.0 * x2 + x1 - 3.0) - 3.0 * x3 * (x2 - 2.0);
+			cE = 4.0 * p * d * (d2 + 7.0 * p2 - 4.0);
+			cP = 3.0 * x3 * rx1;
+			etad = 0.5 * inv_pi * (kap1 + p2 * (p2 + 2.0 * d2) * kap0 - (1.0 + 5.0 * p2 + d2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
+			add = (d < p) ? 2.0 / 3.0 : 0.0;
+			elliptic = true;
+		} else if (p <= 1.0 && d <= (1.0 - p)) {
+			// planet fully inside the disc
 			etad = p2 * 0.5 * (p2 + 2.0 * d2);
 			lambdae = p2;
-		} else if (d > 0.5) {
-			ellke_fast(0.5 * rp_inv, mode, Kk, Ek);
-			lambdad = 1.0 / 3.0 + (16.0 / 9.0) * p * inv_pi * (2.0 * p2 - 1.0) * Ek -
-				  (32.0 * p2 * p2 - 20.0 * p2 + 3.0) * (1.0 / 9.0) * inv_pi * rp_inv * Kk;
-			etad = 0.5 * inv_pi * (kap1 + p2 * (p2 + 2.0 * d2) * kap0 - (1.0 + 5.0 * p2 + d2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
-		} else {
-			lambdad = 1.0 / 3.0 - 4.0 * inv_pi / 9.0;
-			etad = 3.0 / 32.0;
+			const double r1 = rcp_nr(1.0 - x1);
+			q2 = (x2 - x1) * r1;
+			const double rx1 = rcp_nr(x1);
+			nn = x2 * rx1 - 1.0;
+			pref = (2.0 / 9.0) * inv_pi * sqrt(r1);
+			cK = 1.0 - 5.0 * d2 + p2 + x3 * x3;
+			cE = (1.0 - x1) * (d2 + 7.0 * p2 - 4.0);
+			cP = 3.0 * x3 * rx1;
+			add = (d < p) ? 2.0 / 3.0 : 0.0;
+			elliptic = true;
 		}
-		return 1.0 - (w1 * lambdae + w2 * lambdad + c2 * etad) * inv_omega;
 	}
-	if ((d > 0.5 + fabs(p - 0.5) && d < 1.0 + p) || (p > 0.5 && d > fabs(1.0 - p) && d < p)) {
-		const double rdp = rcp_nr(d * p);
-		const double q = sqrt((1.0 - x1) * 0.25 * rdp);
+	// converged part: every lane of the warp that needs K, E, Pi computes them here together
+	if (elliptic) {
+		const double q = sqrt(q2);
 		double Kk, Ek;
 		ellke_fast(q, mode, Kk, Ek);
-		const double rx1 = rcp_nr(x1);
-		const double Pk = ellpic_fast(rx1 - 1.0, q, pitol);
-		lambdad = (1.0 / 9.0) * inv_pi * sqrt(rdp) *
-			  (((1.0 - x2) * (2.0 * x2 + x1 - 3.0) - 3.0 * x3 * (x2 - 2.0)) * Kk + 4.0 * p * d * (d2 + 7.0 * p2 - 4.0) * Ek -
-			   3.0 * x3 * rx1 * Pk);
-		if (d < p) lambdad += 2.0 / 3.0;
-		etad = 0.5 * inv_pi * (kap1 + p2 * (p2 + 2.0 * d2) * kap0 - (1.0 + 5.0 * p2 + d2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
-		return 1.0 - (w1 * lambdae + w2 * lambdad + c2 * etad) * inv_omega;
-	}
-	if (p <= 1.0 && d <= (1.0 - p)) {
-		etad = p2 * 0.5 * (p2 + 2.0 * d2);
-		lambdae = p2;
-		const double r1 = rcp_nr(1.0 - x1);
-		const double q = sqrt((x2 - x1) * r1);
-		double Kk, Ek;
-		ellke_fast(q, mode, Kk, Ek);
-		const double rx1 = rcp_nr(x1);
-		const double Pk = ellpic_fast(x2 * rx1 - 1.0, q, pitol);
-		lambdad = (2.0 / 9.0) * inv_pi * sqrt(r1) *
-			  ((1.0 - 5.0 * d2 + p2 + x3 * x3) * Kk + (1.0 - x1) * (d2 + 7.0 * p2 - 4.0) * Ek - 3.0 * x3 * rx1 * Pk);
-		if (fabs(p + d - 1.0) <= tol)
+		const double Pk = ellpic_fast(nn, q, pitol);
+		lambdad = pref * (cK * Kk + cE * Ek - cP * Pk);
+		if (p <= 1.0 && d <= (1.0 - p) && fabs(p + d - 1.0) <= tol)  // planet edge touches the limb from inside
 			lambdad = (2.0 / 3.0) * inv_pi * acos(1.0 - 2.0 * p) - (4.0 / 9.0) * inv_pi * sqrt(p * (1.0 - p)) * (3.0 + 2.0 * p - 8.0 * p2);
-		if (d < p) lambdad += 2.0 / 3.0;
+		lambdad += add;
 	}
-	return 1.0 - (w1 * lambdae + w2 * lambdad + c2 * etad) * inv_omega;
+	if (!done) result = 1.0 - (w1 * lambdae + w2 * lambdad + c2 * etad) * inv_omega;
+	return result;
 }
 
 // ---------------------------------------------------------------- transit: geometry

@@ -390,9 +390,15 @@ struct GPCore {
 
 // One celerite step in carry form with prepared inputs: phi (per term), U, V (= cos, sin pairs),
 // residual y and diagonal A.  ACC: accumulate quad / log-det (inside the chunk proper).
-template <int NT, bool ACC>
+struct NoMid {
+	__device__ __forceinline__ void operator()() const {}
+};
+
+// mid(): independent work (the preparation of the next step) placed, in program order, inside the
+// narrow part of the dependent chain (reduction -> D -> reciprocal) so the scheduler can fill it.
+template <int NT, bool ACC, typename Mid = NoMid>
 __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], const double (&U)[2 * NT],
-					const double (&V)[2 * NT], double y, double Avar)
+					const double (&V)[2 * NT], double y, double Avar, Mid mid = Mid())
 {
 	constexpr int J = 2 * NT;
 	double pp_[NT * (NT + 1) / 2];
@@ -408,20 +414,29 @@ __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], 
 	double f[J];
 #pragma unroll
 	for (int i = 0; i < J; i++) f[i] = phi[i / 2] * S.g[i];
-	// t = S U (two partial sums per row), D = A - U.t, z = y - U.f (pairwise trees)
-	double tv[J];
+	// t = S U (two partial sums per row; column-outer order so consecutive FMAs share U_j in the
+	// operand-reuse cache), D = A - U.t, z = y - U.f (pairwise trees)
+	double tv[J], acc0[J], acc1[J];
 #pragma unroll
 	for (int i = 0; i < J; i++) {
-		double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-		for (int j = 0; j < J; j += 2) {
-			double s0_ = (i <= j) ? S.P[tri(i, j, J)] : S.P[tri(j, i, J)];
-			double s1_ = (i <= j + 1) ? S.P[tri(i, j + 1, J)] : S.P[tri(j + 1, i, J)];
-			acc0 = fma(s0_, U[j], acc0);
-			acc1 = fma(s1_, U[j + 1], acc1);
-		}
-		tv[i] = acc0 + acc1;
+		acc0[i] = 0.0;
+		acc1[i] = 0.0;
 	}
+#pragma unroll
+	for (int j = 0; j < J; j += 2) {
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double s0_ = (i <= j) ? S.P[tri(i, j, J)] : S.P[tri(j, i, J)];
+			acc0[i] = fma(s0_, U[j], acc0[i]);
+		}
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double s1_ = (i <= j + 1) ? S.P[tri(i, j + 1, J)] : S.P[tri(j + 1, i, J)];
+			acc1[i] = fma(s1_, U[j + 1], acc1[i]);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < J; i++) tv[i] = acc0[i] + acc1[i];
 	double utp[NT], zpp[NT];
 #pragma unroll
 	for (int k = 0; k < NT; k++) {
@@ -438,13 +453,13 @@ __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], 
 	const double z = y - zp;
 	S.notpd |= !(D > 0.0);
 	const double invD = fast_rcp(D);
-	// w = (V - t)/D ; P' = S + (V - t) w^T ; g' = f + w z
 	double vt[J], wv[J];
 #pragma unroll
-	for (int i = 0; i < J; i++) {
-		vt[i] = V[i] - tv[i];
-		wv[i] = vt[i] * invD;
-	}
+	for (int i = 0; i < J; i++) vt[i] = V[i] - tv[i];
+	mid();
+	// w = (V - t)/D ; P' = S + (V - t) w^T ; g' = f + w z
+#pragma unroll
+	for (int i = 0; i < J; i++) wv[i] = vt[i] * invD;
 #pragma unroll
 	for (int i = 0; i < J; i++) {
 #pragma unroll
@@ -471,8 +486,17 @@ struct FastCoef {
 	double c[NT], d[NT], phi0[NT], cr0[NT], sr0[NT];  // exp(-c dt0), cos(d dt0), sin(d dt0)
 };
 
+#ifndef GP_UNROLL
+#define GP_UNROLL 2
+#endif
+#define GP_STR2(x) #x
+#define GP_STR(x) GP_STR2(x)
+#define GP_PRAGMA_UNROLL _Pragma(GP_STR(unroll GP_UNROLL))
+#ifndef GP_MINBLOCKS
+#define GP_MINBLOCKS 2
+#endif
 template <int NT, bool TRANSIT>
-__global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
+__global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(ChunkArgs A)
 {
 	constexpr int J = 2 * NT;
 	constexpr int NP = J * (J + 1) / 2;
@@ -639,40 +663,44 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 2) gp_chunk_kernel(ChunkArgs A)
 		if (order != 0 && st.tilereg[tl]) {
 			// ---- fast loop: every step of this tile is a regular-cadence step.  Straight-line body:
 			// the dependent chain of step n and the preparation of step n+1 are independent.
-			double mvN = load_mean(min(s0 + 1, s1 - 1));  // model value of the NEXT sample, in flight
+			// model values of the next two samples, in flight
+			double mvN = load_mean(min(s0 + 1, s1 - 1)), mvNN = load_mean(min(s0 + 2, s1 - 1));
 			auto fast_range = [&](int a_, int b_, auto acc_tag, auto order_tag) {
 				constexpr bool ACC = decltype(acc_tag)::value;
 				constexpr int ORDER = decltype(order_tag)::value;
-#pragma unroll 2
+GP_PRAGMA_UNROLL
 				for (int n = a_; n < b_; n++) {
 					const int m = min(n + 1, s1 - 1);
-					const double mv2 = load_mean(min(n + 2, s1 - 1));
+					const double mv3 = load_mean(min(n + 3, s1 - 1));
 					const double4 sm = tile[m];
 					const double ddt = sm.x - st.dt0;
-					double phiN[NT], UN[J], VN[J];
+					double phiN[NT], UN[J], VN[J], yN, AN;
+					auto prepare = [&]() {
 #pragma unroll
-					for (int k = 0; k < NT; k++) {
-						const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
-						double cr, sr;
-						if (ORDER == 1) {
-							phiN[k] = fma(-K.phi0[k], xc, K.phi0[k]);
-							cr = fma(-K.sr0[k], xd, K.cr0[k]);
-							sr = fma(K.cr0[k], xd, K.sr0[k]);
-						} else {
-							phiN[k] = K.phi0[k] * fma(fma(0.5, xc, -1.0), xc, 1.0);
-							const double h = fma(-0.5 * xd, xd, 1.0);
-							cr = fma(-K.sr0[k], xd, K.cr0[k] * h);
-							sr = fma(K.cr0[k], xd, K.sr0[k] * h);
+						for (int k = 0; k < NT; k++) {
+							const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
+							double cr, sr;
+							if (ORDER == 1) {
+								phiN[k] = fma(-K.phi0[k], xc, K.phi0[k]);
+								cr = fma(-K.sr0[k], xd, K.cr0[k]);
+								sr = fma(K.cr0[k], xd, K.sr0[k]);
+							} else {
+								phiN[k] = K.phi0[k] * fma(fma(0.5, xc, -1.0), xc, 1.0);
+								const double h = fma(-0.5 * xd, xd, 1.0);
+								cr = fma(-K.sr0[k], xd, K.cr0[k] * h);
+								sr = fma(K.cr0[k], xd, K.sr0[k] * h);
+							}
+							VN[2 * k] = fma(VC[2 * k], cr, -(VC[2 * k + 1] * sr));
+							VN[2 * k + 1] = fma(VC[2 * k + 1], cr, VC[2 * k] * sr);
+							UN[2 * k] = fma(UC[2 * k], cr, -(UC[2 * k + 1] * sr));
+							UN[2 * k + 1] = fma(UC[2 * k + 1], cr, UC[2 * k] * sr);
 						}
-						VN[2 * k] = fma(VC[2 * k], cr, -(VC[2 * k + 1] * sr));
-						VN[2 * k + 1] = fma(VC[2 * k + 1], cr, VC[2 * k] * sr);
-						UN[2 * k] = fma(UC[2 * k], cr, -(UC[2 * k + 1] * sr));
-						UN[2 * k + 1] = fma(UC[2 * k + 1], cr, UC[2 * k] * sr);
-					}
-					const double yN = residual_mv(sm, mvN);
-					mvN = mv2;
-					const double AN = sm.z + asum;
-					gp_step<NT, ACC>(S, phiC, UC, VC, yC, AC);
+						yN = residual_mv(sm, mvN);
+						AN = sm.z + asum;
+					};
+					gp_step<NT, ACC>(S, phiC, UC, VC, yC, AC, prepare);
+					mvN = mvNN;
+					mvNN = mv3;
 #pragma unroll
 					for (int k = 0; k < NT; k++) phiC[k] = phiN[k];
 #pragma unroll
