@@ -78,9 +78,10 @@ struct gpt_engine {
 	int opt_verify = 1;
 	int opt_halo_auto = 1;
 	int opt_ctas_per_sm = 1;
-	double opt_min_chunk_halos = 0.75;  // chunk length >= this many halos
+	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
 	double opt_tol = 1e-10;   // budget for the chunk-coupling error, relative to quad and to logdet
-	int cur_halo = 192;
+	int cur_halo = 0;         // 0: derive from the priors at the first evaluation
+	double prior_cmin = 0.0;  // smallest celerite decay rate c the priors allow (rad per megasecond)
 
 	// stats
 	long long n_launch = 0, n_pass2_calls = 0, n_pass2_chunks = 0, n_evals = 0;
@@ -219,20 +220,48 @@ static int check_stars(gpt_engine *e, int star0, int nstars)
 	return GPT_OK;
 }
 
-// chunk geometry: a whole number of CTA waves over the 148 SMs ("ctas_per_sm" per SM), but never
-// chunks much shorter than the halo they each have to recompute
-static void pick_geometry(gpt_engine *e, int N, int W, int nstars, int &nchunks, int &L, int &H)
+// chunk geometry: "ctas_per_sm" warps per SM sub-partition worth of (walker, chunk) threads, but never
+// chunks shorter than "min_chunk_halos" halos (each chunk recomputes one halo)
+static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, int &nchunks, int &L, int &H)
 {
-	H = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
+	if (e->opt_halo > 0) {
+		H = e->opt_halo;
+	} else {
+		if (e->cur_halo <= 0) {
+			// first evaluation: 1e-12 decay of the slowest mode the priors allow, exp(-c_min dt0) per step
+			double dt0 = std::fabs(e->stars[star0].dt0);
+			double h = (e->prior_cmin > 0 && dt0 > 0) ? std::log(1e12) / (e->prior_cmin * dt0) : 192.0;
+			e->cur_halo = (int)std::min(8192.0, std::max(64.0, std::ceil(h / 16.0) * 16.0));
+		}
+		H = e->cur_halo;
+	}
 	int nc;
 	if (e->opt_chunks > 0) {
 		nc = e->opt_chunks;
 	} else {
-		long long ctas_per_layer = (long long)nstars * ((W + CHUNK_THREADS - 1) / CHUNK_THREADS);
-		long long target = 148LL * std::max(1, e->opt_ctas_per_sm);
-		nc = (int)std::max<long long>(1, target / ctas_per_layer);
-		int maxc = std::max(1, (int)(N / std::max(e->opt_min_chunk_halos * H, 64.0)));
-		nc = std::min(nc, maxc);
+		// Cost model (measured on B200): every thread runs N/nc + H dependent steps; up to one warp
+		// per SM sub-partition they all run concurrently at the single-warp step time, two resident
+		// warps share the FP64 pipe at 1.32x the single-warp throughput, more warps queue up.
+		const int cthreads = std::min(CHUNK_THREADS, ((W + 31) / 32) * 32);
+		const double wpl = (double)nstars * ((W + cthreads - 1) / cthreads) * (cthreads / 32);  // warps per chunk layer
+		const double slots = 148.0 * 4.0;
+		const int nc_max = std::max(1, N / 32);
+		double best = 1e300;
+		nc = 1;
+		for (int cand = 1; cand <= nc_max; cand = cand < 16 ? cand + 1 : (int)std::ceil(cand * 1.08)) {
+			const double h = cand == 1 ? 0.0 : (double)H;
+			const double wps = cand * wpl / slots;
+			double slow = 1.0;
+			if (wps > 1.0) slow = wps <= 2.0 ? 1.0 + (wps - 1.0) * (2.0 / 1.32 - 1.0) : wps / 1.32;
+			const double cost = ((double)N / cand + h) * slow + 0.05 * cand;
+			if (cost < best * 0.999) {
+				best = cost;
+				nc = cand;
+			}
+		}
+		// snap to whole waves when close to one
+		const double per_wave = slots / wpl;
+		if (per_wave >= 1.0 && nc > 0.8 * per_wave && nc < 1.25 * per_wave) nc = (int)per_wave;
 	}
 	nc = std::max(1, std::min(nc, N));
 	L = (N + nc - 1) / nc;
@@ -240,22 +269,25 @@ static void pick_geometry(gpt_engine *e, int N, int W, int nstars, int &nchunks,
 	if (nchunks == 1) H = 0;
 }
 
+// threads per chunk CTA: one per walker of the star, a whole number of warps, at most 128
+static int chunk_threads(int W) { return std::min(CHUNK_THREADS, ((W + 31) / 32) * 32); }
+
 template <int NT>
-static void launch_chunk_nt(bool transit, dim3 grid, cudaStream_t st, const ChunkArgs &a)
+static void launch_chunk_nt(bool transit, dim3 grid, int threads, cudaStream_t st, const ChunkArgs &a)
 {
 	if (transit)
-		gp_chunk_kernel<NT, true><<<grid, CHUNK_THREADS, 0, st>>>(a);
+		gp_chunk_kernel<NT, true><<<grid, threads, 0, st>>>(a);
 	else
-		gp_chunk_kernel<NT, false><<<grid, CHUNK_THREADS, 0, st>>>(a);
+		gp_chunk_kernel<NT, false><<<grid, threads, 0, st>>>(a);
 }
 
-static void launch_chunk(int nt, bool transit, dim3 grid, cudaStream_t st, const ChunkArgs &a)
+static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStream_t st, const ChunkArgs &a)
 {
 	switch (nt) {
-	case 1: launch_chunk_nt<1>(transit, grid, st, a); break;
-	case 2: launch_chunk_nt<2>(transit, grid, st, a); break;
-	case 3: launch_chunk_nt<3>(transit, grid, st, a); break;
-	case 4: launch_chunk_nt<4>(transit, grid, st, a); break;
+	case 1: launch_chunk_nt<1>(transit, grid, threads, st, a); break;
+	case 2: launch_chunk_nt<2>(transit, grid, threads, st, a); break;
+	case 3: launch_chunk_nt<3>(transit, grid, threads, st, a); break;
+	case 4: launch_chunk_nt<4>(transit, grid, threads, st, a); break;
 	default: break;
 	}
 }
@@ -300,7 +332,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	e->timer_end(TK_PREP);
 	e->n_launch++;
 	if (m.has_transit) {
-		dim3 g((N + TR_THREADS - 1) / TR_THREADS, nwalk);
+		dim3 g(nwalk, (N + TR_THREADS - 1) / TR_THREADS);
 		e->timer_begin(TK_TRANSIT);
 		CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), st));
 		e->timer_begin(TK_TRSCAN);
@@ -326,7 +358,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	}
 
 	int nchunks, L, H;
-	pick_geometry(e, N, W, nstars, nchunks, L, H);
+	pick_geometry(e, star0, N, W, nstars, nchunks, L, H);
 	e->last_chunks = nchunks;
 	e->last_L = L;
 	e->last_H = H;
@@ -341,9 +373,10 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
 	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p;
 	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
-	dim3 grid(nchunks, (W + CHUNK_THREADS - 1) / CHUNK_THREADS, nstars);
+	const int cthreads = chunk_threads(W);
+	dim3 grid(nchunks, (W + cthreads - 1) / cthreads, nstars);
 	e->timer_begin(TK_CHUNK);
-	launch_chunk(nt, m.has_transit != 0, grid, st, a);
+	launch_chunk(nt, m.has_transit != 0, grid, cthreads, st, a);
 	e->timer_end(TK_CHUNK);
 	e->n_launch++;
 
@@ -389,7 +422,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			// path can enqueue it unconditionally (no host round trip inside a sampler step)
 			a.pass2 = 1;
 			e->timer_begin(TK_PASS2);
-			launch_chunk(nt, m.has_transit != 0, grid, st, a);
+			launch_chunk(nt, m.has_transit != 0, grid, cthreads, st, a);
 			f.verify = 0;
 			f.skip_if_clean = 1;
 			gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
@@ -606,6 +639,29 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *d)
 		m.tr_fixed[i] = d->tr_fixed[i];
 		m.tr_free[i] = d->tr_free[i];
 	}
+	// slowest decay rate inside the prior box: granulation c = 2 pi b / sqrt(2); bump c = 2 pi nu / (2 Q)
+	{
+		auto lo = [&](int i) { const gpt_prior &p = d->priors[i]; return p.kind == GPT_PRIOR_NORMAL ? p.a - 3 * p.b : p.a; };
+		auto hi = [&](int i) { const gpt_prior &p = d->priors[i]; return p.kind == GPT_PRIOR_NORMAL ? p.a + 3 * p.b : p.b; };
+		double cmin = 0.0;
+		int i = 0;
+		for (int c = 0; c < d->ncomp; c++) {
+			double cc = 0.0;
+			if (m.comp_type[c] == 0) {
+				cc = 2 * kPi * std::max(lo(i + 1), 1e-300) / std::sqrt(2.0);
+				i += 2;
+			} else if (m.comp_type[c] == 1) {
+				cc = 2 * kPi * std::max(lo(i + 2), 1e-300) / (2.0 * std::max(hi(i + 1), 0.5));
+				i += 3;
+			} else {
+				i += 1;
+				continue;
+			}
+			if (cc > 0 && (cmin == 0.0 || cc < cmin)) cmin = cc;
+		}
+		e->prior_cmin = cmin;
+		e->cur_halo = 0;
+	}
 	e->model = m;
 	e->may_generic = may_generic;
 	e->have_model = true;
@@ -731,7 +787,7 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 	CK(cudaMemcpyAsync(e->d_theta.p, pars9, sizeof(double) * W * 9, cudaMemcpyHostToDevice, e->stream));
 	prep_transit_direct_kernel<<<(W + 127) / 128, 128, 0, e->stream>>>(e->model.exp_time, e->d_theta.p, W, e->d_prep.p,
 									    e->d_flags.p);
-	dim3 g((N + TR_THREADS - 1) / TR_THREADS, W);
+	dim3 g(W, (N + TR_THREADS - 1) / TR_THREADS);
 	transit_scan_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
 							     e->d_qcount.p, e->d_mean.p, 1);
 	transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample,

@@ -242,12 +242,12 @@ __global__ void __launch_bounds__(TR_THREADS)
 transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
 		    unsigned int *qcount, double *out, int dense)
 {
-	const int gw = blockIdx.y;
+	const int gw = blockIdx.x;   // walkers on x (up to 2^31 - 1 blocks), sample blocks on y
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
 	const StarDev st = stars[gw / W];
 	const int N = st.N;
-	const int n = blockIdx.x * TR_THREADS + threadIdx.x;
+	const int n = blockIdx.y * TR_THREADS + threadIdx.x;
 	const double *pp = prep + (size_t)gw * PREP_STRIDE;
 	TransitPars tr;
 	tr.per = pp[PP_TR + 0];
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	__shared__ __align__(8) uint64_t s_bar[NSTAGE];
 
 	const int c = blockIdx.x;
-	const int w = blockIdx.y * CHUNK_THREADS + threadIdx.x;
+	const int w = blockIdx.y * blockDim.x + threadIdx.x;  // blockDim.x = min(128, walkers rounded to a warp)
 	const int star = blockIdx.z;
 	const int gw = star * A.W + w;
 	const StarDev st = A.stars[star];
