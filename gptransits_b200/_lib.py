@@ -66,6 +66,7 @@ SIGNATURES = {
     "gpt_log_prob_multi": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
     "gpt_log_prob_device": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
     "gpt_transit_flux": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp]),
+    "gpt_gp_predict": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int64, _dp, _dp]),
     "gpt_sample": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64,
                              C.c_double, _dp, _dp, _i64p]),
     "gpt_sampler_begin": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, _dp, C.c_int, C.c_uint64, C.c_uint64,

@@ -1042,6 +1042,80 @@ int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, 
 	return gpt_sampler_end(e);
 }
 
+int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x_days, int64_t M, double *mu,
+		   double *var)
+{
+	if (!e || !theta || !x_days || !mu || M < 1) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	int rc = check_stars(e, star, 1);
+	if (rc) return rc;
+	rc = sync_stars(e);
+	if (rc) return rc;
+	const ModelDev &m = e->model;
+	if (m.nterms < 1) {
+		e->set_error("gp_predict: the model has no correlated (SHO) term");
+		return GPT_E_UNSUPPORTED;
+	}
+	const int N = e->stars[star].N, J = 2 * m.nterms;
+	if ((double)N * (double)M > 4e9) {
+		e->set_error("gp_predict: N * M too large for the dense prediction kernel");
+		return GPT_E_UNSUPPORTED;
+	}
+	cudaStream_t st = e->stream;
+	CK(e->d_theta.ensure(std::max<size_t>(m.ndim, (size_t)M)));
+	CK(e->d_prep.ensure(PREP_STRIDE));
+	CK(e->d_flags.ensure(1));
+	CK(e->d_wstatus.ensure(1));
+	CK(e->d_nbad.ensure(1));
+	CK(e->d_verr.ensure(1));
+	DevBuf<double> fac, xs, out;
+	CK(fac.ensure((size_t)N * (2 + 3 * J)));
+	CK(xs.ensure(M));
+	CK(out.ensure(2 * (size_t)M));
+	CK(cudaMemcpyAsync(e->d_theta.p, theta, sizeof(double) * m.ndim, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(xs.p, x_days, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+	const StarDev *dst = e->d_stars.p + star;
+	prep_kernel<<<1, 32, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p);
+	if (m.has_transit) {
+		CK(e->d_mean.ensure(N));
+		CK(e->d_queue.ensure(N));
+		CK(e->d_qcount.ensure(1));
+		CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), st));
+		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);
+		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
+							      e->d_mean.p, 0);
+		transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, st>>>(dst, 1, m.supersample, m.exp_time, m.ellip_mode,
+										e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
+	}
+	PredictArgs a;
+	a.star = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
+	a.nterms = m.nterms; a.N = N; a.transit = m.has_transit;
+	a.D = fac.p; a.alpha = fac.p + N; a.W = fac.p + 2 * (size_t)N; a.U = a.W + (size_t)N * J; a.phi = a.U + (size_t)N * J;
+	a.status = e->d_wstatus.p;
+	predict_factor_kernel<<<1, 32, 0, st>>>(a);
+	predict_points_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(a, xs.p, (long long)M, out.p, var ? out.p + M : nullptr);
+	e->n_launch += 3 + (m.has_transit ? 2 : 0);
+	CK(cudaGetLastError());
+	int status = 0, flags = 0;
+	CK(cudaMemcpyAsync(&status, e->d_wstatus.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&flags, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(mu, out.p, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+	if (var) CK(cudaMemcpyAsync(var, out.p + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	fac.release();
+	xs.release();
+	out.release();
+	if (!(flags & WF_VALID)) {
+		e->set_error("gp_predict: parameter vector outside the prior support");
+		return GPT_E_INVALID;
+	}
+	if (status & WF_NOTPD) {
+		e->set_error("gp_predict: covariance matrix is not positive definite");  // celerite: LinAlgError
+		return GPT_E_INVALID;
+	}
+	return GPT_OK;
+}
+
 int gpt_measure_fp64_peak(gpt_engine *e, double *tflops)
 {
 	if (!e || !tflops) return GPT_E_INVALID;

@@ -1093,6 +1093,164 @@ __global__ void diag_kernel(DiagArgs A)
 	}
 }
 
+// ================================================================== GP conditional prediction
+// celerite GP.predict(y, x, return_var=True) as used by the reference's light-curve figure
+// (plot.py:250-260,322-331): mu* = K*^T K^-1 r, var* = k(0) - K*^T K^-1 K*.  One parameter vector,
+// not a hot path: the factor is built and stored sequentially (one thread), the forward/backward
+// solve gives alpha = K^-1 r, then one thread per prediction point evaluates the kernel row on the
+// fly (mean) and runs the forward substitution with the stored factor (variance).  The white-noise
+// (jitter) term is on K's diagonal only, as in celerite's Term.get_value.
+struct PredictArgs {
+	const StarDev *star;
+	const double *prep;    // row of the single walker
+	const int *flags;
+	const double *mean;    // [N] transit model (ppm), valid inside the window
+	int nterms, N, transit;
+	double *D, *W, *U, *phi;  // [N], [N*J] x3
+	double *alpha;         // [N]
+	int *status;           // [1] WF_NOTPD
+};
+
+__device__ inline void predict_generators(const double *pp, int NT, int typemask, double dt, double x, double *phi,
+					  double *U, double *V)
+{
+	for (int k = 0; k < NT; k++) {
+		const double *co = pp + PP_TERMS + 4 * k;
+		if (typemask & (1 << k)) {
+			phi[2 * k] = exp(-co[2] * dt);
+			phi[2 * k + 1] = exp(-co[3] * dt);
+			U[2 * k] = co[0];
+			U[2 * k + 1] = co[1];
+			V[2 * k] = 1.0;
+			V[2 * k + 1] = 1.0;
+		} else {
+			double e = exp(-co[2] * dt), sd, cd;
+			sincos(co[3] * x, &sd, &cd);
+			phi[2 * k] = e;
+			phi[2 * k + 1] = e;
+			U[2 * k] = co[0] * cd + co[1] * sd;
+			U[2 * k + 1] = co[0] * sd - co[1] * cd;
+			V[2 * k] = cd;
+			V[2 * k + 1] = sd;
+		}
+	}
+}
+
+__global__ void predict_factor_kernel(PredictArgs A)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const StarDev st = *A.star;
+	const double *pp = A.prep;
+	const int NT = A.nterms, J = 2 * NT, N = A.N;
+	const int typemask = (int)pp[PP_TYPEMASK];
+	TransitPars tr;
+	if (A.transit) load_transit(pp, tr);
+	double P[2 * MAX_TERMS][2 * MAX_TERMS], g[2 * MAX_TERMS], U[2 * MAX_TERMS], V[2 * MAX_TERMS], phi[2 * MAX_TERMS],
+		tv[2 * MAX_TERMS], wv[2 * MAX_TERMS], f[2 * MAX_TERMS];
+	for (int i = 0; i < 2 * MAX_TERMS; i++) {
+		g[i] = 0.0;
+		for (int j = 0; j < 2 * MAX_TERMS; j++) P[i][j] = 0.0;
+	}
+	const double asum = pp[PP_ASUM];
+	bool notpd = false;
+	// factor + forward substitution: z_n = r_n - U_n f_n
+	for (int n = 0; n < N; n++) {
+		const double4 sm = st.samp[n];
+		double y = sm.y;
+		if (A.transit && in_transit_window(sm.w, tr)) y -= A.mean[n];
+		predict_generators(pp, NT, typemask, sm.x, sm.w * kDaysToMs, phi, U, V);
+		for (int i = 0; i < J; i++) {
+			f[i] = phi[i] * g[i];
+			for (int j = 0; j < J; j++) P[i][j] *= phi[i] * phi[j];
+		}
+		double D = sm.z + asum, zp = 0.0;
+		for (int i = 0; i < J; i++) {
+			double acc = 0.0;
+			for (int j = 0; j < J; j++) acc = fma(P[i][j], U[j], acc);
+			tv[i] = acc;
+		}
+		for (int i = 0; i < J; i++) {
+			D -= U[i] * tv[i];
+			zp = fma(U[i], f[i], zp);
+		}
+		const double z = y - zp;
+		notpd |= !(D > 0.0);
+		for (int i = 0; i < J; i++) wv[i] = (V[i] - tv[i]) / D;
+		for (int i = 0; i < J; i++) {
+			for (int j = 0; j < J; j++) P[i][j] = fma(D * wv[i], wv[j], P[i][j]);
+			g[i] = fma(wv[i], z, f[i]);
+		}
+		A.D[n] = D;
+		A.alpha[n] = z / D;
+		for (int i = 0; i < J; i++) {
+			A.W[(size_t)n * J + i] = wv[i];
+			A.U[(size_t)n * J + i] = U[i];
+			A.phi[(size_t)n * J + i] = phi[i];
+		}
+	}
+	// backward substitution: alpha_n = (z/D)_n - W_n . f,  f <- phi_{n+1} o (f + U_{n+1} alpha_{n+1})
+	for (int i = 0; i < J; i++) f[i] = 0.0;
+	for (int n = N - 2; n >= 0; n--) {
+		const double an1 = A.alpha[n + 1];
+		double dot = 0.0;
+		for (int i = 0; i < J; i++) {
+			f[i] = A.phi[(size_t)(n + 1) * J + i] * fma(A.U[(size_t)(n + 1) * J + i], an1, f[i]);
+			dot = fma(A.W[(size_t)n * J + i], f[i], dot);
+		}
+		A.alpha[n] -= dot;
+	}
+	*A.status = notpd ? WF_NOTPD : 0;
+}
+
+// one thread per prediction point
+__global__ void predict_points_kernel(PredictArgs A, const double *xs_days, long long M, double *mu, double *var)
+{
+	const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	const StarDev st = *A.star;
+	const double *pp = A.prep;
+	const int NT = A.nterms, J = 2 * NT, N = A.N;
+	const int typemask = (int)pp[PP_TYPEMASK];
+	const double xs = xs_days[m] * kDaysToMs;
+	double f[2 * MAX_TERMS];
+	for (int i = 0; i < J; i++) f[i] = 0.0;
+	double mean = 0.0, quad = 0.0, zprev = 0.0;
+	for (int n = 0; n < N; n++) {
+		const double tau = fabs(xs - st.samp[n].w * kDaysToMs);
+		double k = 0.0;
+		for (int t = 0; t < NT; t++) {
+			const double *co = pp + PP_TERMS + 4 * t;
+			if (typemask & (1 << t)) {
+				k += co[0] * exp(-co[2] * tau) + co[1] * exp(-co[3] * tau);
+			} else {
+				double sd, cd;
+				sincos(co[3] * tau, &sd, &cd);
+				k += exp(-co[2] * tau) * (co[0] * cd + co[1] * sd);
+			}
+		}
+		mean = fma(k, A.alpha[n], mean);
+		if (var) {
+			double dot = 0.0;
+			for (int i = 0; i < J; i++) {
+				if (n > 0) f[i] = A.phi[(size_t)n * J + i] * fma(A.W[(size_t)(n - 1) * J + i], zprev, f[i]);
+				dot = fma(A.U[(size_t)n * J + i], f[i], dot);
+			}
+			const double z = k - dot;
+			quad += z * z / A.D[n];
+			zprev = z;
+		}
+	}
+	mu[m] = mean;
+	if (var) {
+		double k0 = 0.0;
+		for (int t = 0; t < NT; t++) {
+			const double *co = pp + PP_TERMS + 4 * t;
+			k0 += (typemask & (1 << t)) ? co[0] + co[1] : co[0];
+		}
+		var[m] = k0 - quad;
+	}
+}
+
 // ================================================================== sampler
 // State per star: x [W][ndim], lpx [W]; per step: set[W] (0/1), act[2][W/2] index lists.
 struct SamplerDev {

@@ -206,3 +206,17 @@ class Engine:
             self._lib.gpt_device_free(self._h, d_theta)
             self._lib.gpt_device_free(self._h, d_lp)
         return lp, np.array(ms[:], dtype=np.float64)
+
+    # -- GP conditional prediction (celerite GP.predict)
+    def gp_predict(self, theta, x_days, star=0, return_var=True):
+        """mu*, var* of the GP at times x_days for ONE walker vector theta[ndim]; the transit model of
+        theta (if any) is subtracted from the star's data first."""
+        th = _d(theta).reshape(-1)
+        if th.size != self.ndim:
+            raise ValueError(f"theta must have ndim={self.ndim} entries")
+        x = _d(x_days).reshape(-1)
+        mu = np.empty(x.size)
+        var = np.empty(x.size) if return_var else None
+        self._ck(self._lib.gpt_gp_predict(self._h, int(star), _p(th), _p(x), x.size, _p(mu),
+                                          _p(var) if return_var else None))
+        return (mu, var) if return_var else mu

@@ -149,6 +149,12 @@ class Model:
     def log_prob_batch(self, theta, return_parts=False):
         return self._ensure_engine().log_prob(theta, return_parts=return_parts)
 
+    def predict(self, params, x=None, return_var=True):
+        """GP conditional mean (and variance) of the residual `flux - transit(params)` at times x
+        (default: the sample times) -- what plot.py:250-260 gets from celerite's GP.predict."""
+        x = self.lc.time if x is None else np.asarray(x, dtype=float)
+        return self._ensure_engine().gp_predict(np.asarray(params, dtype=float), x, return_var=return_var)
+
     # ------------------------------------------------------------------ sampling
     def sample_initial(self, nwalkers):
         """Prior draws in the reference's order (model.py:257-266): GP block then transit block."""

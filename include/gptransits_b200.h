@@ -121,6 +121,16 @@ int gpt_log_prob_device(gpt_engine *e, int star0, int nstars, const double *thet
  * relative flux (1.0 out of transit). */
 int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double *flux);
 
+/* ---- GP conditional prediction ---------------------------- */
+/* Replaces celerite.GP(kernel).compute(t, yerr); .predict(flux - mean, x, return_var=True) as the
+ * reference's light-curve figure calls it (plot.py:250-260,322-331).  theta[ndim] is ONE walker
+ * vector (the transit part, if any, is subtracted from the data first, as plot.py:246-258 does);
+ * x_days[M] are the prediction times; mu[M] and (optional) var[M] are in the data's flux unit.
+ * Errors: GPT_E_INVALID when theta is outside the prior support or the matrix is not positive
+ * definite (celerite raises LinAlgError). */
+int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x_days, int64_t M, double *mu,
+		   double *var);
+
 /* ---- sampler seam ------------------------------------------------------- */
 /* Replaces emcee.EnsembleSampler(W, ndim, lnlike).run_mcmc(init, nsteps)
  * (model.py:270-284) with the default StretchMove(a) for nstars independent

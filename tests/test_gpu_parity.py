@@ -442,3 +442,43 @@ def test_sampler_posterior_agrees_with_cpu_sampler(engine, kic_lc, kic_config):
     assert np.all(np.abs(med_a - med_b) < 0.35 * 0.5 * (wid_a + wid_b)), (med_a, med_b, wid_a)
     assert np.all(np.abs(wid_a / wid_b - 1) < 0.3), (wid_a, wid_b)
     assert abs(nacc.mean() - onacc.mean()) / nsteps < 0.05
+
+
+def test_gp_predict_against_dense_linear_algebra(engine, sim_lc, sim_config):
+    """celerite GP.predict semantics: mu* = K*^T K^-1 r, var* = k(0) - K*^T K^-1 K* (dense check)."""
+    from scipy.linalg import cho_factor, cho_solve
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config, "cosi")
+    sel = slice(0, 400)
+    t, y = t[sel], y[sel] - 1e6
+    yerr = np.full(t.size, 40.0)
+    theta = np.array([249.7, 5.19, 105.8, 368.6, 68.3, 88.7, 5.9, 3.0, 0.05, 10.0, 0.02])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    xs = np.concatenate([t[:50] + 0.004, np.linspace(t[0] - 0.3, t[-1] + 0.3, 123)])
+    mu, var = engine.gp_predict(theta, xs)
+    # dense reference
+    coef = oracle.gp_coeffs(spec["comp_type"], theta[:6])
+
+    def kern(tau):
+        tau = np.abs(tau)
+        k = np.zeros_like(tau)
+        for a, b, c, d in zip(coef["a_comp"], coef["b_comp"], coef["c_comp"], coef["d_comp"]):
+            k += np.exp(-c * tau) * (a * np.cos(d * tau) + b * np.sin(d * tau))
+        return k
+    x = t * 0.0864
+    K = kern(x[:, None] - x[None, :]) + np.diag(yerr ** 2 + coef["jitter"])
+    pars = tr.batman_params(theta[6:], inc_mode=1)
+    resid = y - (oracle.light_curve(t, pars, 6, spec["exp_time"]) - 1) * 1e6
+    Ks = kern(xs[:, None] * 0.0864 - x[None, :])
+    cf = cho_factor(K, lower=True)
+    mu_d = Ks @ cho_solve(cf, resid)
+    var_d = kern(np.zeros(1))[0] - np.einsum("mn,nm->m", Ks, cho_solve(cf, Ks.T))
+    assert np.max(np.abs(mu - mu_d)) < 1e-8 * np.max(np.abs(mu_d))
+    assert np.max(np.abs(var - var_d)) < 1e-8 * np.max(np.abs(var_d))
+    assert np.all(var > 0)
+    # outside the prior support -> error, like an invalid kernel in celerite
+    bad = theta.copy()
+    bad[1] = 0.2
+    with pytest.raises(Exception):
+        engine.gp_predict(bad, xs)
