@@ -296,7 +296,7 @@ static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStrea
 // host_sync: read the verification verdict back and launch pass 2 only when needed; otherwise pass 2
 // is always enqueued (it exits immediately when nothing was flagged) so the sequence is graph-safe.
 static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
-			double *d_parts, bool host_sync)
+			double *d_parts, bool host_sync, const PrepPropose *propose = nullptr)
 {
 	int rc = check_stars(e, star0, nstars);
 	if (rc) return rc;
@@ -324,17 +324,19 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		CK(e->d_qcount.ensure(1));
 	}
 
-	CK(cudaMemsetAsync(e->d_wstatus.p, 0, sizeof(int) * nwalk, st));
-	CK(cudaMemsetAsync(e->d_nbad.p, 0, sizeof(int), st));
-	CK(cudaMemsetAsync(e->d_verr.p, 0, sizeof(double), st));
 	e->timer_begin(TK_PREP);
-	prep_kernel<<<(nwalk + 127) / 128, 128, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p);
+	PrepReset reset;
+	reset.wstatus = e->d_wstatus.p; reset.nbad = e->d_nbad.p; reset.verr = e->d_verr.p;
+	reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
+	PrepPropose pr;
+	memset(&pr, 0, sizeof(pr));
+	if (propose) pr = *propose;
+	prep_kernel<<<(nwalk + 63) / 64, 64, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
 	e->timer_end(TK_PREP);
 	e->n_launch++;
 	if (m.has_transit) {
 		dim3 g(nwalk, (N + TR_THREADS - 1) / TR_THREADS);
 		e->timer_begin(TK_TRANSIT);
-		CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), st));
 		e->timer_begin(TK_TRSCAN);
 		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 							      e->d_mean.p, 0);
@@ -887,18 +889,17 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		sampler_split_kernel<<<ns, 256, (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st>>>(S, e->s_step);
 		e->n_launch++;
 		for (int half = 0; half < 2; half++) {
-			sampler_propose_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
-			e->n_launch++;
-			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false);
+			PrepPropose pr;
+			pr.enabled = 1;
+			pr.half = half;
+			pr.step = e->s_step;
+			pr.S = S;
+			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false, &pr);
 			if (rc) return rc;
-			sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half);
+			sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half, keep ? e->s_kept : -1LL);
 			e->n_launch++;
 		}
-		if (keep) {
-			sampler_record_kernel<<<(ns * W + 127) / 128, 128, 0, st>>>(S, e->s_kept);
-			e->n_launch++;
-			e->s_kept++;
-		}
+		if (keep) e->s_kept++;
 		if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
 		e->s_step++;
 	}
@@ -1075,12 +1076,20 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 	CK(cudaMemcpyAsync(e->d_theta.p, theta, sizeof(double) * m.ndim, cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(xs.p, x_days, sizeof(double) * M, cudaMemcpyHostToDevice, st));
 	const StarDev *dst = e->d_stars.p + star;
-	prep_kernel<<<1, 32, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p);
 	if (m.has_transit) {
 		CK(e->d_mean.ensure(N));
 		CK(e->d_queue.ensure(N));
 		CK(e->d_qcount.ensure(1));
-		CK(cudaMemsetAsync(e->d_qcount.p, 0, sizeof(unsigned int), st));
+	}
+	{
+		PrepReset reset;
+		reset.wstatus = e->d_wstatus.p; reset.nbad = e->d_nbad.p; reset.verr = e->d_verr.p;
+		reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
+		PrepPropose pr;
+		memset(&pr, 0, sizeof(pr));
+		prep_kernel<<<1, 32, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
+	}
+	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);
 		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 							      e->d_mean.p, 0);

@@ -84,12 +84,77 @@ struct ChunkPartial {
 };
 
 // ================================================================== prep
+// State per star: x [W][ndim], lpx [W]; per step: set[W] (0/1), act[2][W/2] index lists.
+struct SamplerDev {
+	double *x;        // [nstars][W][ndim] current positions
+	double *lpx;      // [nstars][W]
+	double *q;        // [nstars][W/2][ndim] proposals of the active half
+	double *lq;       // [nstars][W/2]
+	double *fac;      // [nstars][W/2]  (ndim-1) ln z
+	int *act;         // [nstars][2][W/2] walker ids of each half, ascending
+	long long *nacc;  // [nstars][W]
+	const int *star_ids;  // [nstars] global ids for the RNG key
+	double *chain;    // [nstars][W][cap][ndim]
+	double *logp;     // [nstars][cap][W]
+	int W, ndim, nstars;
+	long long cap;    // chain capacity in steps
+	unsigned long long seed;
+	double a;
+};
+
+
+// stretch proposal of active walker gi: q = c_j - (c_j - s) z,  z = ((a-1) u + 1)^2 / a
+__device__ inline void sampler_propose_one(const SamplerDev &S, unsigned long long step, int half, int gi)
+{
+	const int H = S.W / 2;
+	const int star = gi / H, i = gi - star * H;
+	const uint32_t sid = (uint32_t)S.star_ids[star];
+	const int w = S.act[((size_t)star * 2 + half) * H + i];
+	uint32_t r[4], r2[4];
+	rng_words(S.seed, sid, step, (uint32_t)w, 1, r);
+	rng_words(S.seed, sid, step, (uint32_t)w, 2, r2);
+	double uz = u53(r[0], r[1]);
+	double zz = (S.a - 1.0) * uz + 1.0;
+	zz = zz * zz / S.a;
+	S.fac[gi] = (S.ndim - 1.0) * log(zz);
+	int j = S.act[((size_t)star * 2 + (1 - half)) * H + (int)(((unsigned long long)r2[0] * (unsigned long long)H) >> 32)];
+	const double *xs = S.x + ((size_t)star * S.W + w) * S.ndim;
+	const double *xc = S.x + ((size_t)star * S.W + j) * S.ndim;
+	double *qq = S.q + (size_t)gi * S.ndim;
+	for (int d = 0; d < S.ndim; d++) {
+		double cj = xc[d];
+		qq[d] = cj - (cj - xs[d]) * zz;
+	}
+}
+
+// per-evaluation scratch that prep_kernel clears (replaces four memset nodes per evaluation)
+struct PrepReset {
+	int *wstatus;          // [nwalk]
+	int *nbad;             // [1]
+	double *verr;          // [1]
+	unsigned int *qcount;  // [1] or null
+};
+// optional fused stretch-move proposal: theta must then be S.q
+struct PrepPropose {
+	int enabled;
+	int half;
+	unsigned long long step;
+	SamplerDev S;
+};
+
 // One thread per walker.  theta [nwalk][ndim]; prep [nwalk][PREP_STRIDE]; flags [nwalk].
 __global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep,
-			    int *flags)
+			    int *flags, PrepReset R, PrepPropose PR)
 {
 	int gw = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gw == 0) {
+		if (R.nbad) *R.nbad = 0;
+		if (R.verr) *R.verr = 0.0;
+		if (R.qcount) *R.qcount = 0;
+	}
 	if (gw >= nwalk) return;
+	if (R.wstatus) R.wstatus[gw] = 0;
+	if (PR.enabled) sampler_propose_one(PR.S, PR.step, PR.half, gw);  // writes theta row gw (= S.q)
 	const double *th = theta + (size_t)gw * m.ndim;
 	double *pp = prep + (size_t)gw * PREP_STRIDE;
 	const StarDev st = stars[gw / W];
@@ -1252,24 +1317,6 @@ __global__ void predict_points_kernel(PredictArgs A, const double *xs_days, long
 }
 
 // ================================================================== sampler
-// State per star: x [W][ndim], lpx [W]; per step: set[W] (0/1), act[2][W/2] index lists.
-struct SamplerDev {
-	double *x;        // [nstars][W][ndim] current positions
-	double *lpx;      // [nstars][W]
-	double *q;        // [nstars][W/2][ndim] proposals of the active half
-	double *lq;       // [nstars][W/2]
-	double *fac;      // [nstars][W/2]  (ndim-1) ln z
-	int *act;         // [nstars][2][W/2] walker ids of each half, ascending
-	long long *nacc;  // [nstars][W]
-	const int *star_ids;  // [nstars] global ids for the RNG key
-	double *chain;    // [nstars][W][cap][ndim]
-	double *logp;     // [nstars][cap][W]
-	int W, ndim, nstars;
-	long long cap;    // chain capacity in steps
-	unsigned long long seed;
-	double a;
-};
-
 // one block per star: random half/half split (emcee RedBlueMove with randomize_split=True)
 __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 {
@@ -1302,34 +1349,18 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 	}
 }
 
-// one thread per active walker: stretch proposal q = c_j - (c_j - s) z
+// one thread per active walker: stretch proposal (standalone form; the sampler fuses it into prep_kernel)
 __global__ void sampler_propose_kernel(SamplerDev S, unsigned long long step, int half)
 {
-	const int H = S.W / 2;
 	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gi >= S.nstars * H) return;
-	const int star = gi / H, i = gi - star * H;
-	const uint32_t sid = (uint32_t)S.star_ids[star];
-	const int w = S.act[((size_t)star * 2 + half) * H + i];
-	uint32_t r[4], r2[4];
-	rng_words(S.seed, sid, step, (uint32_t)w, 1, r);
-	rng_words(S.seed, sid, step, (uint32_t)w, 2, r2);
-	double uz = u53(r[0], r[1]);
-	double zz = (S.a - 1.0) * uz + 1.0;
-	zz = zz * zz / S.a;
-	S.fac[gi] = (S.ndim - 1.0) * log(zz);
-	int j = S.act[((size_t)star * 2 + (1 - half)) * H + (int)(((unsigned long long)r2[0] * (unsigned long long)H) >> 32)];
-	const double *xs = S.x + ((size_t)star * S.W + w) * S.ndim;
-	const double *xc = S.x + ((size_t)star * S.W + j) * S.ndim;
-	double *qq = S.q + (size_t)gi * S.ndim;
-	for (int d = 0; d < S.ndim; d++) {
-		double cj = xc[d];
-		qq[d] = cj - (cj - xs[d]) * zz;
-	}
+	if (gi >= S.nstars * (S.W / 2)) return;
+	sampler_propose_one(S, step, half, gi);
 }
 
-// accept/reject: lnpdiff = (ndim-1) ln z + lp(q) - lp(s) > ln u
-__global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int half)
+// accept/reject: lnpdiff = (ndim-1) ln z + lp(q) - lp(s) > ln u.  A walker's position is final for this
+// step once its own half has been decided, so the same thread appends it to the device chain
+// (slot >= 0) -- no separate record launch.
+__global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int half, long long slot)
 {
 	const int H = S.W / 2;
 	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1341,13 +1372,22 @@ __global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int
 	rng_words(S.seed, sid, step, (uint32_t)w, 1, r);
 	double ua = u53(r[2], r[3]);
 	double lq = S.lq[gi];
-	double lnpdiff = S.fac[gi] + lq - S.lpx[(size_t)star * S.W + w];
-	if (lnpdiff > log(ua)) {
-		double *xs = S.x + ((size_t)star * S.W + w) * S.ndim;
+	const size_t gwk = (size_t)star * S.W + w;
+	double lpw = S.lpx[gwk];
+	double lnpdiff = S.fac[gi] + lq - lpw;
+	double *xs = S.x + gwk * S.ndim;
+	const bool acc = lnpdiff > log(ua);
+	if (acc) {
 		const double *qq = S.q + (size_t)gi * S.ndim;
 		for (int d = 0; d < S.ndim; d++) xs[d] = qq[d];
-		S.lpx[(size_t)star * S.W + w] = lq;
-		S.nacc[(size_t)star * S.W + w] += 1;
+		S.lpx[gwk] = lq;
+		S.nacc[gwk] += 1;
+		lpw = lq;
+	}
+	if (slot >= 0) {
+		double *c = S.chain + (gwk * S.cap + slot) * S.ndim;
+		for (int d = 0; d < S.ndim; d++) c[d] = xs[d];
+		S.logp[((size_t)star * S.cap + slot) * S.W + w] = lpw;
 	}
 }
 

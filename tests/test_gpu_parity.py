@@ -482,3 +482,38 @@ def test_gp_predict_against_dense_linear_algebra(engine, sim_lc, sim_config):
     bad[1] = 0.2
     with pytest.raises(Exception):
         engine.gp_predict(bad, xs)
+
+
+def test_four_terms_and_odd_walker_counts(engine):
+    """J = 8 (four SHO terms, the largest register-resident state) and walker counts that are not a
+    multiple of the warp / CTA size (300 walkers = 3 CTAs per chunk, last one partly empty)."""
+    cfg4 = C3_CONFIG_GP[:3] + [
+        {"type": "oscillation_bump", "params": {"values": {"P_g": [False, None, "uniform", 20, 80],
+                                                           "Q": [False, None, "uniform", 1.5, 4.0],
+                                                           "nu_max": [False, None, "uniform", 230, 270]}}},
+        C3_CONFIG_GP[3]]
+    t, y, yerr = synthetic_star(6000, 21)
+    np.random.seed(9)
+    gp = GPModel(cfg4)
+    spec = build_spec(gp, None)
+    theta = gp.sample_prior(37)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    for chunks in (1, 7, 0):
+        engine.set_option("chunks", chunks)
+        _, parts = engine.log_prob(theta, return_parts=True)
+        assert_parts_close(parts, want)
+    engine.set_option("chunks", 0)
+    # 300 walkers, three-term model with transit
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    gp3 = GPModel(C3_CONFIG_GP)
+    spec3 = build_spec(gp3, tr)
+    theta3 = np.hstack([gp3.sample_prior(300), tr.sample_prior(300)])
+    engine.set_model(spec3)
+    engine.upload_star(0, t, y, yerr)
+    lp = engine.log_prob(theta3)
+    want3 = oracle.log_prob(spec3, t, y, yerr, theta3, nthreads=8)
+    assert rel(lp, want3) < RTOL
