@@ -42,7 +42,8 @@ constexpr int PP_INVPER = 33;   // 1 / per (window test uses a multiply, identic
 constexpr int PP_MAXCD = 34;
 constexpr int PP_SININC = 35;   // sin(inc)
 constexpr int PP_RPINV = 36;    // 1 / |rp|
-constexpr int PP_INVOMEGA = 37; // 1 / (1 - u1/3 - u2/6)    // max |c|, |d| over terms (selects the cadence-jitter series order)
+constexpr int PP_INVOMEGA = 37; // 1 / (1 - u1/3 - u2/6)
+constexpr int PP_WOVERPI = 38;  // w / pi    // max |c|, |d| over terms (selects the cadence-jitter series order)
 
 struct ModelDev {
 	int ncomp;
@@ -321,10 +322,11 @@ __device__ __forceinline__ double rcp_nr(double d)
 	return fma(r, e, r);
 }
 
-__device__ inline void ellke_fast(double k, int mode, double &Kk, double &Ek)
+__device__ inline void ellke_fast(double k, int mode, double &Kk, double &Ek, double &m1_out)
 {
+	m1_out = 1.0 - k * k;
 	if (mode == 0) {
-		const double m1 = 1.0 - k * k;
+		const double m1 = m1_out;
 		const double lg = log(m1);
 		const double ek1 = 1.38629436112 + m1 * (0.09666344259 + m1 * (0.03590092383 + m1 * (0.03742563713 + m1 * 0.01451196212)));
 		const double ek2 = (0.5 + m1 * (0.12498593597 + m1 * (0.06880248576 + m1 * (0.03328355346 + m1 * 0.00441787012)))) * lg;
@@ -338,11 +340,13 @@ __device__ inline void ellke_fast(double k, int mode, double &Kk, double &Ek)
 	}
 }
 
-__device__ inline double ellpic_fast(double n, double k, double tol)
+// Bulirsch iteration of batman's ellpic_bulirsch(n, k) with kc^2 = 1 - k^2, p0 = sqrt(n + 1) and
+// 1/p0 supplied by the caller (both are closed forms of the geometry, no square root needed)
+__device__ inline double ellpic_fast(double kc2, double p0, double rp0, double tol)
 {
-	double kc = sqrt(1. - k * k);
-	double p = sqrt(n + 1.);
-	double m0 = 1., c = 1., d = rcp_nr(p), e = kc, f, g;
+	double kc = sqrt(kc2);
+	double p = p0;
+	double m0 = 1., c = 1., d = rp0, e = kc, f, g;
 	for (int nit = 0; nit < 10000; nit++) {
 		const double rp = rcp_nr(p);
 		f = c;
@@ -360,6 +364,17 @@ __device__ inline double ellpic_fast(double n, double k, double tol)
 		}
 	}
 	return 0.0;
+}
+
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	const double h = 0.5 * x;
+	double e = fma(-h * y, y, 0.5);
+	y = fma(y, e, y);
+	e = fma(-h * y, y, 0.5);
+	return fma(y, e, y);
 }
 
 // rp_inv = 1/p, inv_omega = 1/(1 - c1/3 - c2/6): per-walker constants.
@@ -381,7 +396,7 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 	const double pitol = mode == 0 ? 1.0e-8 : 1.0e-10;
 
 	double lambdad = 0.0, etad = 0.0, lambdae = 0.0, kap0 = 0.0, kap1 = 0.0;
-	double q2 = 0.0, nn = 0.0, pref = 0.0, cK = 0.0, cE = 0.0, cP = 0.0, add = 0.0;
+	double q2 = 0.0, ep0 = 1.0, erp0 = 1.0, pref = 0.0, cK = 0.0, cE = 0.0, cP = 0.0, add = 0.0;
 	bool elliptic = false, done = false;
 	double result = 1.0;
 
@@ -401,14 +416,14 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 		}
 		if (d == p) {
 			// planet edge at the stellar centre (measure-zero set): closed forms in K, E only
-			double Kk, Ek;
+			double Kk, Ek, m1_;
 			if (d < 0.5) {
-				ellke_fast(2.0 * p, mode, Kk, Ek);
+				ellke_fast(2.0 * p, mode, Kk, Ek, m1_);
 				lambdad = 1.0 / 3.0 + (2.0 / 9.0) * inv_pi * (4.0 * (2.0 * p2 - 1.0) * Ek + (1.0 - 4.0 * p2) * Kk);
 				etad = p2 * 0.5 * (p2 + 2.0 * d2);
 				lambdae = p2;
 			} else if (d > 0.5) {
-				ellke_fast(0.5 * rp_inv, mode, Kk, Ek);
+				ellke_fast(0.5 * rp_inv, mode, Kk, Ek, m1_);
 				lambdad = 1.0 / 3.0 + (16.0 / 9.0) * p * inv_pi * (2.0 * p2 - 1.0) * Ek -
 					  (32.0 * p2 * p2 - 20.0 * p2 + 3.0) * (1.0 / 9.0) * inv_pi * rp_inv * Kk;
 				etad = 0.5 * inv_pi * (kap1 + p2 * (p2 + 2.0 * d2) * kap0 - (1.0 + 5.0 * p2 + d2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
@@ -418,11 +433,14 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 			}
 		} else if ((d > 0.5 + fabs(p - 0.5) && d < 1.0 + p) || (p > 0.5 && d > fabs(1.0 - p) && d < p)) {
 			// ingress / egress
-			const double rdp = rcp_nr(d * p);
+			const double rsdp = rsqrt_nr(d * p);
+			const double rdp = rsdp * rsdp;
 			q2 = (1.0 - x1) * 0.25 * rdp;
-			const double rx1 = rcp_nr(x1);
-			nn = rx1 - 1.0;
-			pref = (1.0 / 9.0) * inv_pi * sqrt(rdp);
+			const double rpd = rcp_nr(fabs(p - d));   // n + 1 = 1 / x1  ->  sqrt(n + 1) = 1 / |p - d|
+			const double rx1 = rpd * rpd;
+			ep0 = rpd;
+			erp0 = fabs(p - d);
+			pref = (1.0 / 9.0) * inv_pi * rsdp;
 			cK = (1.0 - x2) * (2.0 * x2 + x1 - 3.0) - 3.0 * x3 * (x2 - 2.0);
 			cE = 4.0 * p * d * (d2 + 7.0 * p2 - 4.0);
 			cP = 3.0 * x3 * rx1;
@@ -433,11 +451,14 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 			// planet fully inside the disc
 			etad = p2 * 0.5 * (p2 + 2.0 * d2);
 			lambdae = p2;
-			const double r1 = rcp_nr(1.0 - x1);
+			const double rs1 = rsqrt_nr(1.0 - x1);
+			const double r1 = rs1 * rs1;
 			q2 = (x2 - x1) * r1;
-			const double rx1 = rcp_nr(x1);
-			nn = x2 * rx1 - 1.0;
-			pref = (2.0 / 9.0) * inv_pi * sqrt(r1);
+			const double rpd = rcp_nr(fabs(p - d));   // n + 1 = x2 / x1  ->  sqrt(n + 1) = (p + d) / |p - d|
+			const double rx1 = rpd * rpd;
+			ep0 = (p + d) * rpd;
+			erp0 = fabs(p - d) * rcp_nr(p + d);
+			pref = (2.0 / 9.0) * inv_pi * rs1;
 			cK = 1.0 - 5.0 * d2 + p2 + x3 * x3;
 			cE = (1.0 - x1) * (d2 + 7.0 * p2 - 4.0);
 			cP = 3.0 * x3 * rx1;
@@ -448,9 +469,9 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 	// converged part: every lane of the warp that needs K, E, Pi computes them here together
 	if (elliptic) {
 		const double q = sqrt(q2);
-		double Kk, Ek;
-		ellke_fast(q, mode, Kk, Ek);
-		const double Pk = ellpic_fast(nn, q, pitol);
+		double Kk, Ek, m1;
+		ellke_fast(q, mode, Kk, Ek, m1);
+		const double Pk = ellpic_fast(m1, ep0, erp0, pitol);
 		lambdad = pref * (cK * Kk + cE * Ek - cP * Pk);
 		if (p <= 1.0 && d <= (1.0 - p) && fabs(p + d - 1.0) <= tol)  // planet edge touches the limb from inside
 			lambdad = (2.0 / 3.0) * inv_pi * acos(1.0 - 2.0 * p) - (4.0 / 9.0) * inv_pi * sqrt(p * (1.0 - p)) * (3.0 + 2.0 * p - 8.0 * p2);
@@ -465,7 +486,7 @@ struct TransitPars {
 	double per, t0, rp, a, inc, ecc, w, u1, u2;  // batman semantics, angles in radians
 	double tp;                                   // time of periastron (batman _rsky.c)
 	double wcen, whalf, inv_per;                 // conservative in-transit window
-	double sin_inc, rp_inv, inv_omega;           // per-walker constants of the throughput variant
+	double sin_inc, rp_inv, inv_omega, w_over_pi; // per-walker constants of the throughput variant
 };
 
 __device__ inline double kepler_E(double M, double e)
@@ -511,19 +532,20 @@ __device__ inline double rsky_one(double t, const TransitPars &tr)
 // throughput variant of rsky_one: reciprocal period, per-walker sin(inc), no division for e == 0
 __device__ inline double rsky_fast(double t, const TransitPars &tr)
 {
-	double f;
-	if (tr.ecc < 1.0e-5) {
-		double ph = (t - tr.tp) * tr.inv_per;
-		f = (ph - trunc(ph)) * 2. * kPi;
-	} else {
-		double M = (2. * kPi * tr.inv_per) * (t - tr.tp);
-		double E = kepler_E(M, tr.ecc);
-		f = 2. * atan(sqrt((1. + tr.ecc) / (1. - tr.ecc)) * tan(E / 2.));
-	}
-	const double sf = sin(tr.w + f);
+	double sf, r = tr.a;
 	const double si = tr.sin_inc;
-	double r = tr.a;
-	if (tr.ecc != 0.0) r = tr.a * (1.0 - tr.ecc * tr.ecc) / (1.0 + tr.ecc * cos(f));
+	if (tr.ecc < 1.0e-5) {
+		const double ph = (t - tr.tp) * tr.inv_per;
+		const double fr = ph - trunc(ph);              // f = 2 pi fr
+		sf = sinpi(fma(2.0, fr, tr.w_over_pi));         // sin(w + f)
+		if (tr.ecc != 0.0) r = tr.a * (1.0 - tr.ecc * tr.ecc) / (1.0 + tr.ecc * cospi(2.0 * fr));
+	} else {
+		const double M = (2. * kPi * tr.inv_per) * (t - tr.tp);
+		const double E = kepler_E(M, tr.ecc);
+		const double f = 2. * atan(sqrt((1. + tr.ecc) / (1. - tr.ecc)) * tan(E / 2.));
+		sf = sin(tr.w + f);
+		r = tr.a * (1.0 - tr.ecc * tr.ecc) / (1.0 + tr.ecc * cos(f));
+	}
 	const double d = r * sqrt(1.0 - sf * sf * si * si);
 	return (si * sf > 0.) ? d : 100.;
 }
@@ -555,6 +577,7 @@ __device__ inline void transit_window(TransitPars &tr, double exp_time)
 	tr.sin_inc = sin(tr.inc);
 	tr.rp_inv = 1.0 / fabs(tr.rp);
 	tr.inv_omega = 1.0 / (1.0 - tr.u1 / 3.0 - tr.u2 / 6.0);
+	tr.w_over_pi = tr.w / kPi;
 	double p = fabs(tr.rp);
 	double rmin = tr.a * (1.0 - tr.ecc);
 	if (!(tr.ecc >= 0.0 && tr.ecc < 0.99) || !(rmin > 0.0) || !(p < 90.0) || !(fabs(tr.per) > 0.0) ||
@@ -593,6 +616,12 @@ __device__ __forceinline__ bool in_transit_window(double t, double wcen, double 
 __device__ __forceinline__ bool in_transit_window(double t, const TransitPars &tr)
 {
 	return in_transit_window(t, tr.wcen, tr.inv_per, tr.whalf);
+}
+
+// np.linspace(-e/2, e/2, s)[i] from start = -e/2, step = e/(s-1) (the last point is exactly +e/2)
+__device__ __forceinline__ double supersample_offset(int i, int ss, double start, double step)
+{
+	return (i == ss - 1) ? -start : fma((double)i, step, start);
 }
 
 // exposure-averaged flux at sample time t (batman supersampling: linspace(-e/2, e/2, s) offsets)

@@ -77,6 +77,7 @@ struct gpt_engine {
 	int opt_chunks = 0;      // 0 = auto
 	int opt_verify = 1;
 	int opt_halo_auto = 1;
+	int opt_epoch_scan = 1;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
 	double opt_tol = 1e-10;   // budget for the chunk-coupling error, relative to quad and to logdet
@@ -338,8 +339,16 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		dim3 g(nwalk, (N + TR_THREADS - 1) / TR_THREADS);
 		e->timer_begin(TK_TRANSIT);
 		e->timer_begin(TK_TRSCAN);
-		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
-							      e->d_mean.p, 0);
+		if (e->opt_epoch_scan)
+		{
+			// one thread per transit epoch: a few per 256 samples at most for any realistic period
+			int et = 32;
+			while (et < TR_THREADS && et * 256 < N) et *= 2;
+			transit_epoch_scan_kernel<<<nwalk, et, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p);
+		}
+		else
+			transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
+								      e->d_mean.p, 0);
 		e->timer_end(TK_TRSCAN);
 		transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode,
 								    e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
@@ -512,6 +521,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_ctas_per_sm = std::max(1, (int)value);
 	} else if (k == "min_chunk_halos") {
 		e->opt_min_chunk_halos = value;
+	} else if (k == "epoch_scan") {
+		e->opt_epoch_scan = value != 0;
 	} else if (k == "halo_auto") {
 		e->opt_halo_auto = value != 0;
 	} else if (k == "verify_tol") {

@@ -240,6 +240,7 @@ __global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const doubl
 		pp[PP_SININC] = tr.sin_inc;
 		pp[PP_RPINV] = tr.rp_inv;
 		pp[PP_INVOMEGA] = tr.inv_omega;
+		pp[PP_WOVERPI] = tr.w_over_pi;
 		if (tr.whalf >= 0.5) fl |= WF_TR_ALL;
 	}
 	flags[gw] = fl;
@@ -257,6 +258,7 @@ __device__ inline void load_transit(const double *pp, TransitPars &tr)
 	tr.sin_inc = pp[PP_SININC];
 	tr.rp_inv = pp[PP_RPINV];
 	tr.inv_omega = pp[PP_INVOMEGA];
+	tr.w_over_pi = pp[PP_WOVERPI];
 }
 
 // Direct batman-semantics parameters (gpt_transit_flux): pars9 [nwalk][9] -> prep rows
@@ -288,6 +290,7 @@ __global__ void prep_transit_direct_kernel(double exp_time, const double *pars9,
 	pp[PP_SININC] = tr.sin_inc;
 	pp[PP_RPINV] = tr.rp_inv;
 	pp[PP_INVOMEGA] = tr.inv_omega;
+	pp[PP_WOVERPI] = tr.w_over_pi;
 	flags[gw] = WF_VALID | (tr.whalf >= 0.5 ? WF_TR_ALL : 0);
 }
 
@@ -333,6 +336,67 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 	if (inw) queue[base + __popc(mask & ((1u << lane) - 1))] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n;
 }
 
+// Epoch form of the scan (sparse output only): one CTA per walker, one thread per transit epoch.
+// The thread brackets its epoch's window in the sorted time array by bisection (slightly widened),
+// then applies the SAME per-sample test as the consumers to the few candidates, so the queue holds
+// exactly the samples for which the GP kernels will read mean[].  Walkers whose window covers
+// everything are swept by the whole CTA.
+__global__ void __launch_bounds__(TR_THREADS)
+transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
+			  unsigned int *qcount)
+{
+	const int gw = blockIdx.x;
+	const int fl = flags[gw];
+	if (!(fl & WF_VALID)) return;
+	const StarDev st = stars[gw / W];
+	const int N = st.N;
+	const double *pp = prep + (size_t)gw * PREP_STRIDE;
+	const double per = pp[PP_TR + 0], wcen = pp[PP_WCEN], whalf = pp[PP_WHALF], inv_per = pp[PP_INVPER];
+	const double *t = st.tdays;
+	if (whalf < 0.0) return;  // never in transit
+	if (whalf >= 0.5 || !isfinite(per) || !isfinite(wcen) || !isfinite(inv_per)) {
+		// everything (or NaN parameters: the consumers' test passes for NaN) -> all samples
+		for (int n0 = threadIdx.x; n0 < N; n0 += blockDim.x) {
+			const bool inw = in_transit_window(t[n0], wcen, inv_per, whalf);
+			const unsigned mask = __ballot_sync(__activemask(), inw);
+			if (inw) {
+				const int lane = threadIdx.x & 31;
+				const int leader = __ffs(mask) - 1;
+				unsigned int base = 0;
+				if (lane == leader) base = atomicAdd(qcount, (unsigned int)__popc(mask));
+				base = __shfl_sync(mask, base, leader);
+				queue[base + __popc(mask & ((1u << lane) - 1))] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n0;
+			}
+		}
+		return;
+	}
+	const double pa = fabs(per);
+	const double ph0 = (t[0] - wcen) / pa, ph1 = (t[N - 1] - wcen) / pa;
+	const double kminf = floor(fmin(ph0, ph1)) - 1.0, kmaxf = ceil(fmax(ph0, ph1)) + 1.0;
+	if (!(kmaxf - kminf < 2.0e9)) return;  // absurd period: no epoch bookkeeping possible; window tiny anyway
+	const long long kmin = (long long)kminf, kmax = (long long)kmaxf;
+	for (long long k = kmin + threadIdx.x; k <= kmax; k += blockDim.x) {
+		const double tc = wcen + (double)k * pa;
+		const double half = whalf * pa;
+		const double eps = 1e-9 * pa + 1e-12 * fabs(tc);
+		const double lo = tc - half - eps, hi = tc + half + eps;
+		if (hi < t[0] || lo > t[N - 1]) continue;
+		// first sample with t >= lo
+		int a = 0, b = N;
+		while (a < b) {
+			const int mid = (a + b) >> 1;
+			if (t[mid] < lo) a = mid + 1; else b = mid;
+		}
+		int cnt = 0;
+		for (int n = a; n < N && t[n] <= hi; n++) cnt += in_transit_window(t[n], wcen, inv_per, whalf) ? 1 : 0;
+		if (cnt == 0) continue;
+		unsigned int base = atomicAdd(qcount, (unsigned int)cnt);
+		for (int n = a; n < N && t[n] <= hi; n++)
+			if (in_transit_window(t[n], wcen, inv_per, whalf))
+				queue[base++] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n;
+	}
+}
+
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 1
 #endif
@@ -362,7 +426,9 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				N = st.N;
 				TransitPars tr;
 				load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
-				const double ts = supersample_time(st.tdays[n], i, ss, exp_time);
+				// np.linspace offsets: start + i*step is numpy's arange(num)*step + start
+				const double ss_start = -exp_time / 2., ss_step = ss > 1 ? exp_time / (ss - 1) : 0.0;
+				const double ts = ss > 1 ? supersample_offset(i, ss, ss_start, ss_step) + st.tdays[n] : st.tdays[n];
 				f = ma_flux_fast(rsky_fast(ts, tr), tr.rp, tr.rp_inv, tr.u1, tr.u2, tr.inv_omega, mode);
 			}
 			// ordered sum over the group's lanes (np.mean order), gathered by the group's first lane
