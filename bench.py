@@ -300,7 +300,8 @@ def run_ours(args):
         except Exception:
             traffic = None
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers (one untimed call first: allocations)
+    eng.sample(init, 2, seed=args.seed, nstars=nstars)
     barrier()
     t0 = time.perf_counter()
     for s, y in enumerate(ys):
