@@ -80,7 +80,7 @@ struct gpt_engine {
 	int opt_epoch_scan = 1;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
-	double opt_tol = 1e-10;   // budget for the chunk-coupling error, relative to quad and to logdet
+	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
 	int cur_halo = 0;         // 0: derive from the priors at the first evaluation
 	double prior_cmin = 0.0;  // smallest celerite decay rate c the priors allow (rad per megasecond)
 
@@ -162,13 +162,13 @@ struct gpt_engine {
 	void adapt_halo(int H, bool failed, double ratio)
 	{
 		if (!opt_halo_auto || opt_halo != 0 || H <= 0) return;
-		// geometric decay model: error/tolerance ratio r at halo H, O(1e12) at H = 0; aim at 0.1
+		// geometric decay model: error/tolerance ratio r at halo H, O(1e12) at H = 0; aim at 0.3
 		double r = failed ? 1e3 : std::max(ratio, 1e-30);
-		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(0.1);
+		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(0.3);
 		double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
 		int nh = (int)std::ceil(want / 16.0) * 16;
 		nh = std::max(32, std::min(nh, 4096));
-		cur_halo = nh > cur_halo ? nh : std::max(nh, (int)(cur_halo * 0.9));
+		cur_halo = nh > cur_halo ? nh : std::max(nh, (int)(cur_halo * 0.75));
 	}
 
 	void set_error(const std::string &m) { err = m; }
@@ -229,9 +229,10 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 		H = e->opt_halo;
 	} else {
 		if (e->cur_halo <= 0) {
-			// first evaluation: 1e-12 decay of the slowest mode the priors allow, exp(-c_min dt0) per step
+			// first evaluation: 10 decades of decay of the slowest mode the priors allow, exp(-c_min dt0)
+			// per step (measured on C3: the criterion passes after ~9.5 decades); adapted afterwards
 			double dt0 = std::fabs(e->stars[star0].dt0);
-			double h = (e->prior_cmin > 0 && dt0 > 0) ? std::log(1e12) / (e->prior_cmin * dt0) : 192.0;
+			double h = (e->prior_cmin > 0 && dt0 > 0) ? std::log(1e10) / (e->prior_cmin * dt0) : 192.0;
 			e->cur_halo = (int)std::min(8192.0, std::max(64.0, std::ceil(h / 16.0) * 16.0));
 		}
 		H = e->cur_halo;

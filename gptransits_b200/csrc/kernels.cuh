@@ -994,24 +994,34 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			double a = pp[PP_TERMS + 4 * k], b = pp[PP_TERMS + 4 * k + 1];
 			ua[2 * k] = ua[2 * k + 1] = sqrt(a * a + b * b);
 		}
-		// sum of a geometric decay that lost >= 10 decades over the halo: <= H / ln(1e10) ~ H / 23
-		const double G = fmax((double)A.H, 16.0) * (1.0 / 12.0);
 		const double budL = A.tol * fmax(1.0, fabs(logdet)) / A.nchunks;
 		const double budQ = A.tol * fmax(fabs(quad), 1e-300) / A.nchunks;
+		const double Hh = fmax((double)A.H, 16.0);
 		double worst = 0.0;
 		int nbad = 0;
 		for (int k = 1 + tid; k < A.nchunks; k += FIN_THREADS) {
 			const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
 			const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
 			ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
-			double eS = 0.0, ef = 0.0;
+			double eS = 0.0, ef = 0.0, nS = 0.0, nf = 0.0;
 			int idx = 0;
 			for (int i = 0; i < J; i++)
-				for (int j = i; j < J; j++, idx++)
-					eS += (i == j ? 1.0 : 2.0) * ua[i] * ua[j] * fabs(ct[idx] - ce[idx]);
-			for (int i = 0; i < J; i++) ef += ua[i] * fabs(ct[NP + i] - ce[NP + i]);
-			double errL = eS / pr.dmin * G;
-			double errQ = 2.0 * ef * pr.zmax * G;
+				for (int j = i; j < J; j++, idx++) {
+					const double wgt = (i == j ? 1.0 : 2.0) * ua[i] * ua[j];
+					eS += wgt * fabs(ct[idx] - ce[idx]);
+					nS += wgt * fabs(ct[idx]);
+				}
+			for (int i = 0; i < J; i++) {
+				ef += ua[i] * fabs(ct[NP + i] - ce[NP + i]);
+				nf += ua[i] * fabs(ct[NP + i]);
+			}
+			// The halo started from a zero carry, i.e. from an error as large as the state itself, and
+			// left eS (ef) of it after H steps: a geometric decay whose remaining sum over the chunk is
+			// at most H / ln(initial / final) first-step errors (never taken below H / 30).
+			const double GS = Hh / fmin(fmax(log(fmax(nS, 1e-300) / fmax(eS, 1e-300)), 8.0), 30.0);
+			const double Gf = Hh / fmin(fmax(log(fmax(nf, 1e-300) / fmax(ef, 1e-300)), 8.0), 30.0);
+			double errL = eS / pr.dmin * GS;
+			double errQ = 2.0 * ef * pr.zmax * Gf;
 			double r = fmax(errL / budL, errQ / budQ);
 			bool bad = !(r <= 1.0);  // NaN -> redo
 			if (isfinite(r)) worst = fmax(worst, r);
