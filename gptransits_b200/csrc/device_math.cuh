@@ -48,6 +48,8 @@ constexpr int PP_WOVERPI = 38;  // w / pi    // max |c|, |d| over terms (selects
 struct ModelDev {
 	int ncomp;
 	int comp_type[MAX_COMP];
+	int comp_off[MAX_COMP];   // offset of the component's first parameter in theta
+	int comp_term[MAX_COMP];  // index of its SHO term, -1 for white noise
 	int nterms;    // number of SHO terms (granulation + oscillation components)
 	int ndim, ndim_gp;
 	int has_transit;

@@ -333,7 +333,10 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	PrepPropose pr;
 	memset(&pr, 0, sizeof(pr));
 	if (propose) pr = *propose;
-	prep_kernel<<<(nwalk + 63) / 64, 64, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
+	if (nwalk <= 4096)
+		prep_kernel<<<nwalk, PREP_THREADS, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
+	else
+		prep_wide_kernel<<<(nwalk + 63) / 64, 64, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
 	e->timer_end(TK_PREP);
 	e->n_launch++;
 	if (m.has_transit) {
@@ -611,6 +614,8 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *d)
 			return GPT_E_INVALID;
 		}
 		m.comp_type[c] = t;
+		m.comp_off[c] = ndim_gp;
+		m.comp_term[c] = t != GPT_COMP_WHITE_NOISE ? nterms : -1;
 		if (t == GPT_COMP_OSCILLATION_BUMP) {
 			// Q is the second parameter; Q < 1/2 turns the term into two real celerite terms
 			if (ndim_gp + 1 < d->ndim) {
@@ -1099,7 +1104,7 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 		reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
 		PrepPropose pr;
 		memset(&pr, 0, sizeof(pr));
-		prep_kernel<<<1, 32, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
+		prep_kernel<<<1, PREP_THREADS, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
 	}
 	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);

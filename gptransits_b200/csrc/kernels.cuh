@@ -143,7 +143,170 @@ struct PrepPropose {
 };
 
 // One thread per walker.  theta [nwalk][ndim]; prep [nwalk][PREP_STRIDE]; flags [nwalk].
-__global__ void prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep,
+// One CTA of three warps per walker, so that the three independent pieces run concurrently instead
+// of one thread serialising ~50 transcendental calls:
+//   warp 0  priors, one lane per free parameter (and, in the sampler, the stretch proposal, one lane
+//           per dimension, before anything else)
+//   warp 1  celerite coefficients, one lane per GP component
+//   warp 2  transit parameter scatter, time of periastron, in-transit window (lane 0)
+// Sums are gathered in component / parameter order by one lane, so the arithmetic order does not
+// depend on the launch shape.
+constexpr int PREP_THREADS = 96;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep, int *flags,
+	    PrepReset R, PrepPropose PR)
+{
+	__shared__ double s_th[MAX_NDIM];
+	__shared__ double s_lp[2];
+	__shared__ double s_gp[4];  // asum, jit2, maxcd, typemask
+	const int gw = blockIdx.x;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if (gw == 0 && tid == 0) {
+		if (R.nbad) *R.nbad = 0;
+		if (R.verr) *R.verr = 0.0;
+		if (R.qcount) *R.qcount = 0;
+	}
+	if (gw >= nwalk) return;
+	if (tid == 0 && R.wstatus) R.wstatus[gw] = 0;
+	double *pp = prep + (size_t)gw * PREP_STRIDE;
+	const StarDev st = stars[gw / W];
+
+	// ---- theta (optionally the fused stretch proposal q = c_j - (c_j - s) z, one lane per dimension)
+	if (warp == 0) {
+		if (PR.enabled) {
+			const SamplerDev &S = PR.S;
+			const int H = S.W / 2;
+			const int star = gw / H, i = gw - star * H;
+			const uint32_t sid = (uint32_t)S.star_ids[star];
+			const int w = S.act[((size_t)star * 2 + PR.half) * H + i];
+			uint32_t r[4], r2[4];
+			rng_words(S.seed, sid, PR.step, (uint32_t)w, 1, r);
+			rng_words(S.seed, sid, PR.step, (uint32_t)w, 2, r2);
+			double zz = (S.a - 1.0) * u53(r[0], r[1]) + 1.0;
+			zz = zz * zz / S.a;
+			if (lane == 0) S.fac[gw] = (S.ndim - 1.0) * log(zz);
+			const int j = S.act[((size_t)star * 2 + (1 - PR.half)) * H + (int)(((unsigned long long)r2[0] * (unsigned long long)H) >> 32)];
+			if (lane < S.ndim) {
+				const double cj = S.x[((size_t)star * S.W + j) * S.ndim + lane];
+				const double q = cj - (cj - S.x[((size_t)star * S.W + w) * S.ndim + lane]) * zz;
+				S.q[(size_t)gw * S.ndim + lane] = q;
+				s_th[lane] = q;
+			}
+		} else if (lane < m.ndim) {
+			s_th[lane] = theta[(size_t)gw * m.ndim + lane];
+		}
+	}
+	__syncthreads();
+
+	if (warp == 0) {
+		// model.py:300-303 -- both prior sums must be finite
+		double lp = 0.0;
+		if (lane < m.ndim) lp = prior_logpdf(m.prior_kind[lane], m.prior_a[lane], m.prior_b[lane], s_th[lane]);
+		double lp_gp = 0.0, lp_tr = 0.0;
+		for (int i = 0; i < m.ndim; i++) {
+			const double v = __shfl_sync(0xffffffffu, lp, i);
+			if (i < m.ndim_gp) lp_gp += v; else lp_tr += v;
+		}
+		if (lane == 0) {
+			s_lp[0] = lp_gp;
+			s_lp[1] = lp_tr;
+		}
+	} else if (warp == 1) {
+		// gp.py:34-40 + component.py get_parameters_celerite -> celerite coefficients, one lane per component
+		double co[4] = {0, 0, 0, 0};
+		double casum = 0.0, cjit = 0.0, cmax = 0.0;
+		int cmask = 0;
+		if (lane < m.ncomp) {
+			const int i = m.comp_off[lane], term = m.comp_term[lane];
+			bool real_pair = false;
+			if (m.comp_type[lane] == 0) {
+				const double a = s_th[i], b = s_th[i + 1];
+				const double w = b * (2 * kPi);
+				const double S0 = (sqrt(2.0) / (2 * kPi)) * (a * a / b);
+				real_pair = sho_coeffs(log(S0), log(1.0 / sqrt(2.0)), log(w), co);
+			} else if (m.comp_type[lane] == 1) {
+				const double Pg = s_th[i], Q = s_th[i + 1], numax = s_th[i + 2];
+				const double S0 = Pg / (4 * (Q * Q));
+				const double w = numax * (2 * kPi);
+				real_pair = sho_coeffs(log(S0), log(Q), log(w), co);
+			} else {
+				cjit = exp(2.0 * log(s_th[i]));
+			}
+			if (term >= 0) {
+				for (int q = 0; q < 4; q++) pp[PP_TERMS + 4 * term + q] = co[q];
+				casum = real_pair ? co[0] + co[1] : co[0];
+				cmax = fmax(fabs(co[2]), fabs(co[3]));
+				if (real_pair) cmask = 1 << term;
+			}
+		}
+		double asum = 0.0, jit2 = 0.0, maxcd = 0.0;
+		int typemask = 0;
+		for (int c = 0; c < m.ncomp; c++) {
+			asum += __shfl_sync(0xffffffffu, casum, c);
+			jit2 += __shfl_sync(0xffffffffu, cjit, c);
+			maxcd = fmax(maxcd, __shfl_sync(0xffffffffu, cmax, c));
+			typemask |= __shfl_sync(0xffffffffu, cmask, c);
+		}
+		if (lane == 0) {
+			s_gp[0] = asum;
+			s_gp[1] = jit2;
+			s_gp[2] = maxcd;
+			s_gp[3] = (double)typemask;
+		}
+	} else if (warp == 2 && lane == 0 && m.has_transit) {
+		// transit.py:97-106 -- scatter free parameters, map verbatim onto batman's (inc, w in degrees)
+		double pars[9];
+		int k = m.ndim_gp;
+		for (int q = 0; q < 9; q++) pars[q] = m.tr_free[q] ? s_th[k++] : m.tr_fixed[q];
+		TransitPars tr;
+		tr.per = pars[0];
+		tr.t0 = pars[1];
+		tr.rp = fabs(pars[2]);
+		tr.a = pars[3];
+		// transit.py:103 assigns the `cosi` value to batman's inc (degrees) verbatim
+		double inc_deg = m.inc_mode == 1 ? acos(pars[4]) * (180. / kPi) : pars[4];
+		tr.inc = inc_deg * kPi / 180.;
+		tr.ecc = pars[5];
+		tr.w = pars[6] * kPi / 180.;
+		tr.u1 = pars[7];
+		tr.u2 = pars[8];
+		tr.tp = periastron_time(tr.t0, tr.per, tr.ecc, tr.w);
+		transit_window(tr, m.exp_time);
+		double *q = pp + PP_TR;
+		q[0] = tr.per; q[1] = tr.t0; q[2] = tr.rp; q[3] = tr.a; q[4] = tr.inc;
+		q[5] = tr.ecc; q[6] = tr.w; q[7] = tr.u1; q[8] = tr.u2;
+		pp[PP_TP] = tr.tp;
+		pp[PP_WCEN] = tr.wcen;
+		pp[PP_WHALF] = tr.whalf;
+		pp[PP_INVPER] = tr.inv_per;
+		pp[PP_SININC] = tr.sin_inc;
+		pp[PP_RPINV] = tr.rp_inv;
+		pp[PP_INVOMEGA] = tr.inv_omega;
+		pp[PP_WOVERPI] = tr.w_over_pi;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int fl = 0;
+		const double lp_gp = s_lp[0], lp_tr = s_lp[1];
+		if (isfinite(lp_gp) && isfinite(lp_tr)) fl |= WF_VALID;
+		pp[PP_LNPRIOR] = (fl & WF_VALID) ? (lp_tr + lp_gp) : -CUDART_INF;
+		const int typemask = (int)s_gp[3];
+		if (typemask) fl |= WF_GENERIC;
+		// the series used on regular steps need |c * ddt|, |d * ddt| <= 1e-3
+		if (!(s_gp[2] * st.dmax <= 1.0e-3)) fl |= WF_SLOWTRIG;
+		pp[PP_JIT2] = s_gp[1];
+		pp[PP_MAXCD] = s_gp[2];
+		pp[PP_ASUM] = s_gp[1] + s_gp[0];
+		pp[PP_TYPEMASK] = s_gp[3];
+		if (m.has_transit && pp[PP_WHALF] >= 0.5) fl |= WF_TR_ALL;
+		flags[gw] = fl;
+	}
+}
+
+// One thread per walker: the throughput form of prep_kernel for large batches (thousands of
+// walkers, e.g. many stars), where per-walker latency is irrelevant and tiny CTAs would not pay.
+__global__ void prep_wide_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep,
 			    int *flags, PrepReset R, PrepPropose PR)
 {
 	int gw = blockIdx.x * blockDim.x + threadIdx.x;
