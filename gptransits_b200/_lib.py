@@ -74,6 +74,7 @@ SIGNATURES = {
     "gpt_sampler_run": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "gpt_sampler_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp, _dp]),
     "gpt_sampler_state": (C.c_int, [_vp, _dp, _dp, _i64p]),
+    "gpt_sampler_rhat": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
     "gpt_sampler_end": (C.c_int, [_vp]),
     "gpt_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "gpt_sampler_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]),

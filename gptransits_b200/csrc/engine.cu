@@ -1036,6 +1036,32 @@ int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *nacc
 	return GPT_OK;
 }
 
+int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat)
+{
+	if (!e || !rhat || !e->sampling || first < 0 || count < 2 || first + count > e->s_kept) {
+		if (e) e->set_error("sampler_rhat: need at least 2 kept steps inside the kept range");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	const SamplerDev &S = e->S;
+	if (S.W > 1024) {
+		e->set_error("sampler_rhat: more than 1024 walkers per star are not supported");
+		return GPT_E_UNSUPPORTED;
+	}
+	const int nb = S.nstars * S.ndim;
+	DevBuf<double> out;
+	CK(out.ensure(nb));
+	int threads = 32;
+	while (threads < S.W && threads < 256) threads *= 2;
+	sampler_rhat_kernel<<<nb, threads, 2 * sizeof(double) * std::max(threads, S.W), e->stream>>>(S, first, count, out.p);
+	e->n_launch++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(rhat, out.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	out.release();
+	return GPT_OK;
+}
+
 int gpt_sampler_end(gpt_engine *e)
 {
 	if (!e) return GPT_E_INVALID;

@@ -1642,6 +1642,49 @@ __global__ void sampler_record_kernel(SamplerDev S, long long slot)
 	S.logp[((size_t)star * S.cap + slot) * S.W + w] = S.lpx[gi];
 }
 
+// ================================================================== on-device convergence diagnostic
+// Gelman-Rubin statistic of the device-resident chain with the reference's conventions
+// (convergence.py:4-35: V/W without the square root, chain [walker, step, dim]): one block per
+// (star, parameter), one thread per walker, over kept steps [first, first + count).
+__global__ void sampler_rhat_kernel(SamplerDev S, long long first, long long count, double *rhat)
+{
+	extern __shared__ double s_red[];
+	const int star = blockIdx.x / S.ndim, d = blockIdx.x - star * S.ndim;
+	const int W = S.W;
+	double *s_mean = s_red, *s_ss = s_red + blockDim.x;
+	double gm = 0.0;
+	// pass 1: per-walker means
+	for (int w = threadIdx.x; w < W; w += blockDim.x) {
+		const double *c = S.chain + (((size_t)star * W + w) * S.cap + first) * S.ndim + d;
+		double m = 0.0;
+		for (long long n = 0; n < count; n++) m += c[(size_t)n * S.ndim];
+		m /= (double)count;
+		double ss = 0.0;
+		for (long long n = 0; n < count; n++) {
+			const double v = c[(size_t)n * S.ndim] - m;
+			ss += v * v;
+		}
+		s_mean[w] = m;
+		s_ss[w] = ss;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double within = 0.0;
+		for (int w = 0; w < W; w++) {
+			gm += s_mean[w];
+			within += s_ss[w];
+		}
+		gm /= W;
+		double between = 0.0;
+		for (int w = 0; w < W; w++) between += (s_mean[w] - gm) * (s_mean[w] - gm);
+		const double n = (double)count, m = (double)W;
+		between /= (m - 1.0);                 // B / n
+		within /= (m * (n - 1.0));            // W
+		const double V = within * (n - 1.0) / n + between + between / m;
+		rhat[blockIdx.x] = V / within;
+	}
+}
+
 // ================================================================== FP64 peak probe
 __global__ void dfma_peak_kernel(double *out, int iters)
 {

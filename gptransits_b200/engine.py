@@ -173,6 +173,12 @@ class Engine:
         self._ck(self._lib.gpt_sampler_state(self._h, _p(x), _p(lp), na.ctypes.data_as(C.POINTER(C.c_int64))))
         return x, lp, na
 
+    def sampler_rhat(self, first, count):
+        """Gelman-Rubin V/W per (star, parameter) over kept steps [first, first+count), on the device."""
+        out = np.empty((self._sns, self.ndim))
+        self._ck(self._lib.gpt_sampler_rhat(self._h, int(first), int(count), _p(out)))
+        return out
+
     def sampler_end(self):
         self._ck(self._lib.gpt_sampler_end(self._h))
 

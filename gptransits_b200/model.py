@@ -197,6 +197,7 @@ class Model:
         block = int(self.settings.get("checkpoint_every") or remaining) if save else remaining
         block = max(1, min(block, remaining))
         chains, logps = ([chain0] if chain0 is not None else []), ([logp0] if logp0 is not None else [])
+        self.block_rhat = []
         eng.sampler_begin(init, seed=self.settings["seed"], step0=done)
         try:
             while remaining > 0:
@@ -207,6 +208,15 @@ class Model:
                 logps.append(l[0])
                 remaining -= n
                 done += n
+                if n >= 4:
+                    # Gelman-Rubin V/W of this block, computed on the device-resident chain
+                    rhat = eng.sampler_rhat(0, n)[0]
+                    self.block_rhat.append(rhat)
+                    log.info(f"iteration {done}: max Gelman-Rubin V/W over the last {n} steps = {rhat.max():.4f}")
+                    stop = self.settings.get("rhat_stop")
+                    if stop and rhat.max() < stop:
+                        log.info(f"stopping early: V/W below {stop}")
+                        remaining = 0
                 if save:
                     np.savez(state, iteration=done, chain=np.concatenate(chains, axis=1),
                              log_prob=np.concatenate(logps, axis=0))
@@ -215,7 +225,7 @@ class Model:
             eng.sampler_end()
         self.chain = np.concatenate(chains, axis=1)          # (W, nsteps, ndim)   model.py:283
         self.log_prob = np.concatenate(logps, axis=0)        # (nsteps, W)         model.py:284
-        self.acceptance_fraction = nacc[0] / max(1, nsteps - (chain0.shape[1] if chain0 is not None else 0))
+        self.acceptance_fraction = nacc[0] / max(1, self.chain.shape[1] - (chain0.shape[1] if chain0 is not None else 0))
         log.info(f"Mean acceptance fraction: {self.acceptance_fraction.mean():.3f}")
         if save:
             log.info("Saving chain and log_prob")

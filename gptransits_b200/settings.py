@@ -16,6 +16,7 @@ DEFAULT_SETTINGS = {
     "ellip": "batman",         # "batman": Hastings K/E like the reference; "exact"
     "device": 0,
     "checkpoint_every": 1000,
+    "rhat_stop": None,         # stop when the per-block Gelman-Rubin V/W (device-side) falls below this
 }
 
 

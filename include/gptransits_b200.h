@@ -156,6 +156,10 @@ int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_
 int gpt_sampler_run(gpt_engine *e, int64_t nsteps, int keep);
 int gpt_sampler_read(gpt_engine *e, int64_t first, int64_t count, double *chain, double *logp);
 int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *naccept);
+/* Gelman-Rubin statistic V/W (the reference's convention: convergence.py:4-35, no square root) of the
+ * kept steps [first, first + count) of the device chain, per star and parameter: rhat[nstars*ndim].
+ * Replaces pulling the chain to the host for the check at model.py:417-424 while a run is in flight. */
+int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat);
 int gpt_sampler_end(gpt_engine *e);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------ */

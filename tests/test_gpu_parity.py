@@ -517,3 +517,20 @@ def test_four_terms_and_odd_walker_counts(engine):
     lp = engine.log_prob(theta3)
     want3 = oracle.log_prob(spec3, t, y, yerr, theta3, nthreads=8)
     assert rel(lp, want3) < RTOL
+
+
+def test_device_gelman_rubin_matches_host(engine, kic_lc, kic_config):
+    from gptransits_b200 import convergence
+    t, y, yerr, spec, gp = kic_setup(kic_lc, kic_config, baseline_removed=True)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    np.random.seed(4)
+    init = gp.sample_prior(24)
+    engine.sampler_begin(init, seed=11)
+    engine.sampler_run(120, keep=True)
+    chain, _ = engine.sampler_read(0, 120)
+    rhat = engine.sampler_rhat(40, 80)
+    engine.sampler_end()
+    want, _, _ = convergence.gelman_rubin(chain[0][:, 40:120, :])
+    assert rel(rhat[0], want) < 1e-10
