@@ -626,14 +626,4 @@ __device__ __forceinline__ double supersample_offset(int i, int ss, double start
 	return (i == ss - 1) ? -start : fma((double)i, step, start);
 }
 
-// exposure-averaged flux at sample time t (batman supersampling: linspace(-e/2, e/2, s) offsets)
-__device__ inline double supersample_time(double t, int i, int ss, double exp_time)
-{
-	if (ss <= 1) return t;
-	double start = -exp_time / 2., stop = exp_time / 2.;
-	double step = (stop - start) / (ss - 1);
-	double off = (i == ss - 1) ? stop : start + i * step;
-	return off + t;
-}
-
 }  // namespace gpt

@@ -78,6 +78,7 @@ struct gpt_engine {
 	int opt_verify = 1;
 	int opt_halo_auto = 1;
 	int opt_epoch_scan = 1;
+	int opt_transit_strict = 0;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
 	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
@@ -271,6 +272,18 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 	if (nchunks == 1) H = 0;
 }
 
+// flux of the queued (walker, sample) items; "transit_strict" selects batman's own operation order
+static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *stars, int W, int ss, double exp_time,
+				int mode, const double *prep, const unsigned long long *queue, const unsigned int *qcount,
+				double *out, int dense)
+{
+	const int grid = 148 * 2 * TR_MINBLOCKS;
+	if (e->opt_transit_strict)
+		transit_eval_kernel<true><<<grid, TR_THREADS, 0, st>>>(stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+	else
+		transit_eval_kernel<false><<<grid, TR_THREADS, 0, st>>>(stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+}
+
 // threads per chunk CTA: one per walker of the star, a whole number of warps, at most 128
 static int chunk_threads(int W) { return std::min(CHUNK_THREADS, ((W + 31) / 32) * 32); }
 
@@ -354,7 +367,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 								      e->d_mean.p, 0);
 		e->timer_end(TK_TRSCAN);
-		transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, st>>>(dst, W, m.supersample, m.exp_time, m.ellip_mode,
+		launch_transit_eval(e, st, dst, W, m.supersample, m.exp_time, m.ellip_mode,
 								    e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
 		e->timer_end(TK_TRANSIT);
 		e->n_launch += 2;
@@ -525,6 +538,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_ctas_per_sm = std::max(1, (int)value);
 	} else if (k == "min_chunk_halos") {
 		e->opt_min_chunk_halos = value;
+	} else if (k == "transit_strict") {
+		e->opt_transit_strict = value != 0;
 	} else if (k == "epoch_scan") {
 		e->opt_epoch_scan = value != 0;
 	} else if (k == "halo_auto") {
@@ -809,7 +824,7 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 	dim3 g(W, (N + TR_THREADS - 1) / TR_THREADS);
 	transit_scan_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
 							     e->d_qcount.p, e->d_mean.p, 1);
-	transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->model.supersample,
+	launch_transit_eval(e, e->stream, e->d_stars.p + star, W, e->model.supersample,
 								   e->model.exp_time, e->model.ellip_mode, e->d_prep.p,
 								   e->d_queue.p, e->d_qcount.p, e->d_mean.p, 1);
 	e->n_launch += 3;
@@ -1136,7 +1151,7 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);
 		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 							      e->d_mean.p, 0);
-		transit_eval_kernel<<<148 * 2 * TR_MINBLOCKS, TR_THREADS, 0, st>>>(dst, 1, m.supersample, m.exp_time, m.ellip_mode,
+		launch_transit_eval(e, st, dst, 1, m.supersample, m.exp_time, m.ellip_mode,
 										e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
 	}
 	PredictArgs a;

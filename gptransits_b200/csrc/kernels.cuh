@@ -563,6 +563,8 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 1
 #endif
+// STRICT: batman's own operation order (rsky_one + ma_flux) instead of the throughput arrangement
+template <bool STRICT>
 __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS)
 transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep,
 		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense)
@@ -592,7 +594,8 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				// np.linspace offsets: start + i*step is numpy's arange(num)*step + start
 				const double ss_start = -exp_time / 2., ss_step = ss > 1 ? exp_time / (ss - 1) : 0.0;
 				const double ts = ss > 1 ? supersample_offset(i, ss, ss_start, ss_step) + st.tdays[n] : st.tdays[n];
-				f = ma_flux_fast(rsky_fast(ts, tr), tr.rp, tr.rp_inv, tr.u1, tr.u2, tr.inv_omega, mode);
+				f = STRICT ? ma_flux(rsky_one(ts, tr), tr.rp, tr.u1, tr.u2, mode)
+					   : ma_flux_fast(rsky_fast(ts, tr), tr.rp, tr.rp_inv, tr.u1, tr.u2, tr.inv_omega, mode);
 			}
 			// ordered sum over the group's lanes (np.mean order), gathered by the group's first lane
 			double s = f;
@@ -615,7 +618,8 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 			load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
 			double s = 0.0;
 			for (int i = 0; i < ss; i++)
-				s += ma_flux(rsky_one(supersample_time(st.tdays[n], i, ss, exp_time), tr), tr.rp, tr.u1, tr.u2, mode);
+				s += ma_flux(rsky_one(supersample_offset(i, ss, -exp_time / 2., exp_time / (ss - 1)) + st.tdays[n], tr), tr.rp,
+					     tr.u1, tr.u2, mode);
 			double m = s / ss;
 			out[(size_t)gw * st.N + n] = dense ? m : (m - 1) * 1e6;
 		}
@@ -1122,7 +1126,6 @@ __device__ __forceinline__ double block_sum(double v, double *scratch)
 __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 {
 	__shared__ double scratch[FIN_THREADS / 32];
-	__shared__ int s_nbad[FIN_THREADS / 32];
 	const int gw = blockIdx.x;
 	const int tid = threadIdx.x;
 	if (gw >= A.nwalk) return;
@@ -1205,7 +1208,6 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
 			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
-		(void)s_nbad;
 	}
 	if (tid == 0) {
 		const double lnprior = pp[PP_LNPRIOR];
@@ -1588,14 +1590,6 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 	}
 }
 
-// one thread per active walker: stretch proposal (standalone form; the sampler fuses it into prep_kernel)
-__global__ void sampler_propose_kernel(SamplerDev S, unsigned long long step, int half)
-{
-	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gi >= S.nstars * (S.W / 2)) return;
-	sampler_propose_one(S, step, half, gi);
-}
-
 // accept/reject: lnpdiff = (ndim-1) ln z + lp(q) - lp(s) > ln u.  A walker's position is final for this
 // step once its own half has been decided, so the same thread appends it to the device chain
 // (slot >= 0) -- no separate record launch.
@@ -1628,18 +1622,6 @@ __global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int
 		for (int d = 0; d < S.ndim; d++) c[d] = xs[d];
 		S.logp[((size_t)star * S.cap + slot) * S.W + w] = lpw;
 	}
-}
-
-// append the current state to the device chain at slot
-__global__ void sampler_record_kernel(SamplerDev S, long long slot)
-{
-	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gi >= S.nstars * S.W) return;
-	const int star = gi / S.W, w = gi - star * S.W;
-	const double *xs = S.x + (size_t)gi * S.ndim;
-	double *c = S.chain + (((size_t)star * S.W + w) * S.cap + slot) * S.ndim;
-	for (int d = 0; d < S.ndim; d++) c[d] = xs[d];
-	S.logp[((size_t)star * S.cap + slot) * S.W + w] = S.lpx[gi];
 }
 
 // ================================================================== on-device convergence diagnostic
