@@ -31,13 +31,37 @@ class ModelDesc(C.Structure):
                 ("priors", C.POINTER(Prior))]
 
 
+def source_hash():
+    """Hash of everything the library is built from; embedded in the binary (gpt_version)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in SOURCES + [HEADER]:
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def _built_hash(path):
+    """The source hash embedded in a built library, read from the file (no dlopen)."""
+    try:
+        with open(path, "rb") as f:
+            data = f.read()
+        i = data.find(b"(sm_100a, src=")
+        if i < 0:
+            return None
+        return data[i + 14:i + 30].decode()
+    except Exception:
+        return None
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree with nvcc for sm_100a."""
-    newest = max(os.path.getmtime(p) for p in SOURCES + [HEADER])
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+    want = source_hash()
+    if not force and os.path.exists(LIB_PATH) and _built_hash(LIB_PATH) == want:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, SOURCES[0]]
+    cmd = [nvcc] + NVCC_FLAGS + [f'-DGPT_SRC_HASH="{want}"', "-o", LIB_PATH, SOURCES[0]]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
@@ -94,6 +118,12 @@ def lib():
             raise GptError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
         _lib = C.CDLL(LIB_PATH)
+        _lib.gpt_version.restype = C.c_char_p
+        built = _lib.gpt_version().decode()
+        if "GPT_LIB_PATH" not in os.environ and f"src={source_hash()}" not in built:
+            _lib = None
+            raise GptError(f"{LIB_PATH} is stale ({built}; sources now hash to {source_hash()}): rebuild with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(_lib, name)
             fn.restype = res

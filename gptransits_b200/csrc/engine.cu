@@ -465,7 +465,10 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
-const char *gpt_version(void) { return "gptransits_b200 0.1 (sm_100a)"; }
+#ifndef GPT_SRC_HASH
+#define GPT_SRC_HASH "unknown"
+#endif
+const char *gpt_version(void) { return "gptransits_b200 0.1 (sm_100a, src=" GPT_SRC_HASH ")"; }
 
 int gpt_engine_create(int device, gpt_engine **out)
 {
