@@ -92,7 +92,7 @@ struct gpt_engine {
 
 	// evaluation workspaces
 	DevBuf<double> d_theta, d_lp, d_parts, d_prep, d_mean, d_carryT, d_carryE;
-	DevBuf<int> d_flags, d_wstatus;
+	DevBuf<int> d_flags, d_wstatus, d_wbad;
 	DevBuf<ChunkPartial> d_partial;
 	DevBuf<unsigned char> d_redo;
 	DevBuf<unsigned long long> d_queue;  // transit work queue: (walker << 32) | sample
@@ -311,8 +311,10 @@ static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStrea
 // host_sync: read the verification verdict back and launch pass 2 only when needed; otherwise pass 2
 // is always enqueued (it exits immediately when nothing was flagged) so the sequence is graph-safe.
 static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
-			double *d_parts, bool host_sync, const PrepPropose *propose = nullptr)
+			double *d_parts, bool host_sync, const PrepPropose *propose = nullptr,
+			const FinalAccept *accept = nullptr, bool *accept_done = nullptr)
 {
+	if (accept_done) *accept_done = false;
 	int rc = check_stars(e, star0, nstars);
 	if (rc) return rc;
 	rc = sync_stars(e);
@@ -395,6 +397,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	CK(e->d_carryE.ensure((size_t)nwalk * nchunks * CS));
 	CK(e->d_partial.ensure((size_t)nwalk * nchunks));
 	CK(e->d_redo.ensure((size_t)nwalk * nchunks));
+	CK(e->d_wbad.ensure(nwalk));
 
 	ChunkArgs a;
 	a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
@@ -416,7 +419,14 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	f.verify = (nchunks > 1 && e->opt_verify) ? 1 : 0;
 	f.skip_if_clean = 0;
 	f.acc = e->d_acc.p;
+	f.wbad = e->d_wbad.p;
 	f.tol = e->opt_tol;
+	memset(&f.AC, 0, sizeof(f.AC));
+	// the accept/reject can ride on the finalize kernel when every walker's result comes from it
+	if (accept && !e->may_generic && !host_sync) {
+		f.AC = *accept;
+		if (accept_done) *accept_done = true;
+	}
 	e->timer_begin(TK_FINAL);
 	gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
 	e->timer_end(TK_FINAL);
@@ -516,7 +526,7 @@ void gpt_engine_destroy(gpt_engine *e)
 	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
 	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
 	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
-	e->d_queue.release(); e->d_qcount.release();
+	e->d_queue.release(); e->d_qcount.release(); e->d_wbad.release();
 	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
 	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
 	if (e->h_nbad) cudaFreeHost(e->h_nbad);
@@ -929,10 +939,19 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 			pr.half = half;
 			pr.step = e->s_step;
 			pr.S = S;
-			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false, &pr);
+			FinalAccept ac;
+			ac.enabled = 1;
+			ac.half = half;
+			ac.step = e->s_step;
+			ac.slot = keep ? e->s_kept : -1LL;
+			ac.S = S;
+			bool fused = false;
+			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false, &pr, &ac, &fused);
 			if (rc) return rc;
-			sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half, keep ? e->s_kept : -1LL);
-			e->n_launch++;
+			if (!fused) {
+				sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half, ac.slot);
+				e->n_launch++;
+			}
 		}
 		if (keep) e->s_kept++;
 		if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));

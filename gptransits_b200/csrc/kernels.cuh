@@ -143,6 +143,46 @@ struct PrepPropose {
 };
 
 // One thread per walker.  theta [nwalk][ndim]; prep [nwalk][PREP_STRIDE]; flags [nwalk].
+// accept/reject of active walker gi with proposal log-probability lq:
+// lnpdiff = (ndim-1) ln z + lp(q) - lp(s) > ln u.  A walker's position is final for this step once its
+// own half has been decided, so the same thread appends it to the device chain (slot >= 0).
+__device__ inline void sampler_accept_one(const SamplerDev &S, unsigned long long step, int half, int gi, double lq,
+					  long long slot)
+{
+	const int H = S.W / 2;
+	const int star = gi / H, i = gi - star * H;
+	const uint32_t sid = (uint32_t)S.star_ids[star];
+	const int w = S.act[((size_t)star * 2 + half) * H + i];
+	uint32_t r[4];
+	rng_words(S.seed, sid, step, (uint32_t)w, 1, r);
+	const double ua = u53(r[2], r[3]);
+	const size_t gwk = (size_t)star * S.W + w;
+	double lpw = S.lpx[gwk];
+	const double lnpdiff = S.fac[gi] + lq - lpw;
+	double *xs = S.x + gwk * S.ndim;
+	if (lnpdiff > log(ua)) {
+		const double *qq = S.q + (size_t)gi * S.ndim;
+		for (int d = 0; d < S.ndim; d++) xs[d] = qq[d];
+		S.lpx[gwk] = lq;
+		S.nacc[gwk] += 1;
+		lpw = lq;
+	}
+	if (slot >= 0) {
+		double *c = S.chain + (gwk * S.cap + slot) * S.ndim;
+		for (int d = 0; d < S.ndim; d++) c[d] = xs[d];
+		S.logp[((size_t)star * S.cap + slot) * S.W + w] = lpw;
+	}
+}
+
+// optional accept/reject fused into the finalize kernel (one walker per block)
+struct FinalAccept {
+	int enabled;
+	int half;
+	unsigned long long step;
+	long long slot;
+	SamplerDev S;
+};
+
 // One CTA of three warps per walker, so that the three independent pieces run concurrently instead
 // of one thread serialising ~50 transcendental calls:
 //   warp 0  priors, one lane per free parameter (and, in the sampler, the stretch proposal, one lane
@@ -1102,7 +1142,9 @@ struct FinalArgs {
 	int verify;     // 1: compare carries and flag chunks; 0: just reduce
 	int skip_if_clean;  // second invocation: nothing to do when pass 1 flagged no chunk
 	unsigned long long *acc;  // [2] running totals over calls: flagged chunks, max error ratio (bits)
+	int *wbad;      // [nwalk] 1: the walker had a flagged chunk (its result is final only after pass 2)
 	double tol;
+	FinalAccept AC;
 };
 
 // One block of FIN_THREADS per walker; threads stride over chunks / chunk boundaries; the sums use a
@@ -1129,11 +1171,13 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 	const int gw = blockIdx.x;
 	const int tid = threadIdx.x;
 	if (gw >= A.nwalk) return;
-	if (A.skip_if_clean && *A.nbad == 0) return;
+	if (A.skip_if_clean && (*A.nbad == 0 || !A.wbad[gw])) return;  // second invocation: flagged walkers only
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
 	if (!(fl & WF_VALID)) {
 		if (tid == 0) {
+			if (A.wbad) A.wbad[gw] = 0;
+			if (A.AC.enabled) sampler_accept_one(A.AC.S, A.AC.step, A.AC.half, gw, -CUDART_INF, A.AC.slot);
 			A.lp[gw] = -CUDART_INF;
 			if (A.parts) {
 				A.parts[4 * gw + 0] = pp[PP_LNPRIOR];
@@ -1154,6 +1198,7 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 	}
 	const double quad = block_sum(q, scratch);
 	const double logdet = block_sum(ld, scratch);
+	int walker_bad = 0;
 	if (A.verify && A.nchunks > 1) {
 		double ua[2 * MAX_TERMS];
 		for (int k = 0; k < A.nterms; k++) {
@@ -1208,8 +1253,10 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
 			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
+		walker_bad = __syncthreads_or(nbad > 0);
 	}
 	if (tid == 0) {
+		if (!A.skip_if_clean && A.wbad) A.wbad[gw] = walker_bad;
 		const double lnprior = pp[PP_LNPRIOR];
 		double lnl = -0.5 * (quad + logdet + (double)A.N * 1.8378770664093454836);
 		double lp = lnprior + lnl;
@@ -1224,6 +1271,9 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			A.parts[4 * gw + 2] = logdet;
 			A.parts[4 * gw + 3] = lnl;
 		}
+		// a walker without a flagged chunk is final now; a flagged one is decided by the second
+		// invocation, after pass 2 has repaired its chunks
+		if (A.AC.enabled && !walker_bad) sampler_accept_one(A.AC.S, A.AC.step, A.AC.half, gw, lp, A.AC.slot);
 	}
 }
 
@@ -1590,38 +1640,12 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 	}
 }
 
-// accept/reject: lnpdiff = (ndim-1) ln z + lp(q) - lp(s) > ln u.  A walker's position is final for this
-// step once its own half has been decided, so the same thread appends it to the device chain
-// (slot >= 0) -- no separate record launch.
+// standalone accept/reject (models whose log-probability is not produced by gp_finalize_kernel)
 __global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int half, long long slot)
 {
-	const int H = S.W / 2;
 	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gi >= S.nstars * H) return;
-	const int star = gi / H, i = gi - star * H;
-	const uint32_t sid = (uint32_t)S.star_ids[star];
-	const int w = S.act[((size_t)star * 2 + half) * H + i];
-	uint32_t r[4];
-	rng_words(S.seed, sid, step, (uint32_t)w, 1, r);
-	double ua = u53(r[2], r[3]);
-	double lq = S.lq[gi];
-	const size_t gwk = (size_t)star * S.W + w;
-	double lpw = S.lpx[gwk];
-	double lnpdiff = S.fac[gi] + lq - lpw;
-	double *xs = S.x + gwk * S.ndim;
-	const bool acc = lnpdiff > log(ua);
-	if (acc) {
-		const double *qq = S.q + (size_t)gi * S.ndim;
-		for (int d = 0; d < S.ndim; d++) xs[d] = qq[d];
-		S.lpx[gwk] = lq;
-		S.nacc[gwk] += 1;
-		lpw = lq;
-	}
-	if (slot >= 0) {
-		double *c = S.chain + (gwk * S.cap + slot) * S.ndim;
-		for (int d = 0; d < S.ndim; d++) c[d] = xs[d];
-		S.logp[((size_t)star * S.cap + slot) * S.W + w] = lpw;
-	}
+	if (gi >= S.nstars * (S.W / 2)) return;
+	sampler_accept_one(S, step, half, gi, S.lq[gi], slot);
 }
 
 // ================================================================== on-device convergence diagnostic
