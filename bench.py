@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--walkers", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="size of the bounded CPU sample")
@@ -74,6 +74,13 @@ def build_workload(name, rank, args):
         lo = rank * per
         return dict(label=f"C4 1024 synthetic stars x N=4096 x 64 walkers, {per} stars per GPU", t=t,
                     ys=list(y[lo:lo + per]), yerr=s, config=cfg, W=args.walkers or 64, J=6, star_ids=np.arange(lo, lo + per))
+    if name == "c1":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import KIC_CONFIG
+        with np.load(os.path.join(ROOT, "tests", "golden", "example_lightcurves.npz")) as z:
+            t, f, e = z["kic_time"], z["kic_flux"], z["kic_flux_err"]
+        return dict(label="C1 examples/kic-012008916 (N=1292), GP only, 24 walkers", t=t, ys=[f * 1e6 - 1e6],
+                    yerr=e * 1e6, config=KIC_CONFIG, W=args.walkers or 24, J=4, no_inject=True)
     if name == "c2":
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from conftest import SIM_CONFIG
@@ -87,9 +94,19 @@ def build_workload(name, rank, args):
 def model_of(work, t):
     from gptransits_b200 import BatmanModel, GPModel, build_spec
     gp = GPModel(work["config"]["gp"])
-    tr = BatmanModel(work["config"]["transit"][0])
-    tr.init_model(t, t[1] - t[0], 6)
+    tr = None
+    if work["config"].get("transit"):
+        tr = BatmanModel(work["config"]["transit"][0])
+        tr.init_model(t, t[1] - t[0], 6)
     return gp, tr, build_spec(gp, tr)
+
+
+def draw_prior(gp, tr, n):
+    """n walkers from the priors, GP block then transit block (model.py:257-266)."""
+    blocks = [gp.sample_prior(n)]
+    if tr is not None:
+        blocks.append(tr.sample_prior(n))
+    return np.hstack(blocks)
 
 
 def inject_transit(eng, work, spec):
@@ -188,7 +205,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     W = work["W"]
     nsample = args.cpu_evals or min(W, max(2 * cores, 32))
-    theta = np.hstack([gp.sample_prior(nsample), tr.sample_prior(nsample)])
+    theta = draw_prior(gp, tr, nsample)
     for _ in range(args.warmup):
         cpu_evals_per_s(spec, t, y, work["yerr"], theta[:cores], cores)
     times = []
@@ -259,7 +276,7 @@ def run_ours(args):
     for s, y in enumerate(ys):
         eng.upload_star(s, t, y, work["yerr"])
     ndim = spec["prior_kind"].size
-    init = np.hstack([gp.sample_prior(W * nstars), tr.sample_prior(W * nstars)]).reshape(nstars, W, ndim)
+    init = draw_prior(gp, tr, W * nstars).reshape(nstars, W, ndim)
     star_ids = work.get("star_ids")
     flush = not args.no_flush
     peak_tf = eng.fp64_peak_tflops()
@@ -304,7 +321,8 @@ def run_ours(args):
     walkers_per_launch = (W // 2) * nstars
     flops_per_launch = F_GP[J] * N * walkers_per_launch
     achieved_tf = flops_per_launch / (chunk_ms / max(chunk_n, 1) * 1e-3) / 1e12 if chunk_n else None
-    step_tf = (F_GP[J] + F_TR) * N * W * nstars / (float(ms.mean()) * 1e-3) / 1e12
+    f_tr = F_TR if tr is not None else 0.0
+    step_tf = (F_GP[J] + f_tr) * N * W * nstars / (float(ms.mean()) * 1e-3) / 1e12
     # HBM view of the same kernel: algorithmic bytes = star data once per walker group + carries
     bytes_per_launch = 32.0 * N * nstars + walkers_per_launch * (8 * ndim + 32)
     traffic = None
@@ -342,7 +360,7 @@ def run_ours(args):
     if world == 1 and args.batch_walkers > 0:
         WB = args.batch_walkers
         np.random.seed(args.seed + 1000)
-        thb = np.hstack([gp.sample_prior(WB), tr.sample_prior(WB)])
+        thb = draw_prior(gp, tr, WB)
         eng.log_prob(thb[:WB])
         eng.log_prob(thb[:WB])
         eng.set_option("reset_timers", 1)
@@ -354,7 +372,7 @@ def run_ours(args):
         batched = {"walkers": WB, "evals_per_s": WB / (float(np.median(msb)) * 1e-3), "ms": float(np.median(msb)),
                    "kernel_ms": kb, "chunk_tflops": fb / (kb["chunk"] * 1e-3) / 1e12,
                    "chunk_frac": fb / (kb["chunk"] * 1e-3) / 1e12 / peak_tf,
-                   "whole_eval_frac": (F_GP[J] + F_TR) * N * WB / (float(np.median(msb)) * 1e-3) / 1e12 / peak_tf,
+                   "whole_eval_frac": (F_GP[J] + f_tr) * N * WB / (float(np.median(msb)) * 1e-3) / 1e12 / peak_tf,
                    "chunks": eng.stat("chunks"), "chunk_len": eng.stat("chunk_len"), "halo": eng.stat("halo")}
 
     cpu = None

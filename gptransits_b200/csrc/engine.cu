@@ -53,7 +53,8 @@ struct DevBuf {
 struct Star {
 	double4 *samp = nullptr;
 	double *tdays = nullptr;
-	unsigned char *tilereg = nullptr;
+	int *irr = nullptr;
+	int nirr = 0;
 	int N = 0;
 	double dt0 = 0, dreg = 0, dmax = 0;
 	bool has_err = false;
@@ -78,6 +79,7 @@ struct gpt_engine {
 	int opt_verify = 1;
 	int opt_halo_auto = 1;
 	int opt_epoch_scan = 1;
+	int opt_adapt_every = 32;  // sampler steps between halo adaptations
 	int opt_transit_strict = 0;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
@@ -183,7 +185,9 @@ static int sync_stars(gpt_engine *e)
 	for (size_t i = 0; i < h.size(); i++) {
 		h[i].samp = e->stars[i].samp;
 		h[i].tdays = e->stars[i].tdays;
-		h[i].tilereg = e->stars[i].tilereg;
+		h[i].irr = e->stars[i].irr;
+		h[i].nirr = e->stars[i].nirr;
+		h[i]._pad2 = 0;
 		h[i].N = e->stars[i].N;
 		h[i]._pad = 0;
 		h[i].dt0 = e->stars[i].dt0;
@@ -509,7 +513,7 @@ int gpt_star_clear(gpt_engine *e)
 	for (auto &s : e->stars) {
 		if (s.samp) cudaFree(s.samp);
 		if (s.tdays) cudaFree(s.tdays);
-		if (s.tilereg) cudaFree(s.tilereg);
+		if (s.irr) cudaFree(s.irr);
 	}
 	e->stars.clear();
 	e->stars_dirty = true;
@@ -553,6 +557,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_min_chunk_halos = value;
 	} else if (k == "transit_strict") {
 		e->opt_transit_strict = value != 0;
+	} else if (k == "adapt_every") {
+		e->opt_adapt_every = (int)value;
 	} else if (k == "epoch_scan") {
 		e->opt_epoch_scan = value != 0;
 	} else if (k == "halo_auto") {
@@ -724,10 +730,10 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	CK(cudaStreamSynchronize(e->stream));
 	if (s.samp) cudaFree(s.samp);
 	if (s.tdays) cudaFree(s.tdays);
-	if (s.tilereg) cudaFree(s.tilereg);
+	if (s.irr) cudaFree(s.irr);
 	s.samp = nullptr;
 	s.tdays = nullptr;
-	s.tilereg = nullptr;
+	s.irr = nullptr;
 	std::vector<double4> h(N);
 	std::vector<double> dts;
 	dts.reserve(N);
@@ -760,12 +766,12 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	CK(cudaMalloc((void **)&s.samp, sizeof(double4) * N));
 	CK(cudaMemcpy(s.samp, h.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
 	{
-		const int64_t ntiles = (N + TILE - 1) / TILE;
-		std::vector<unsigned char> reg(ntiles, 1);
+		std::vector<int> irr;
 		for (int64_t n = 0; n < N; n++)
-			if (!(std::fabs(h[n].x - dt0) <= dreg)) reg[n / TILE] = 0;
-		CK(cudaMalloc((void **)&s.tilereg, ntiles));
-		CK(cudaMemcpy(s.tilereg, reg.data(), ntiles, cudaMemcpyHostToDevice));
+			if (!(std::fabs(h[n].x - dt0) <= dreg)) irr.push_back((int)n);
+		s.nirr = (int)irr.size();
+		CK(cudaMalloc((void **)&s.irr, sizeof(int) * std::max<size_t>(1, irr.size())));
+		if (!irr.empty()) CK(cudaMemcpy(s.irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
 	}
 	CK(cudaMalloc((void **)&s.tdays, sizeof(double) * N));
 	CK(cudaMemcpy(s.tdays, t_days, sizeof(double) * N, cudaMemcpyHostToDevice));
@@ -926,7 +932,28 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	}
 	CK(e->d_acc.ensure(2));
 	CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
+	// verification verdicts accumulate on the device; every "adapt_every" steps (and at the end) they
+	// are read back -- one small synchronisation -- to steer the halo length
+	auto adapt = [&]() -> int {
+		unsigned long long acc[2] = {0, 0};
+		CK(cudaMemcpyAsync(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
+		CK(cudaStreamSynchronize(st));
+		double ratio;
+		memcpy(&ratio, &acc[1], sizeof(double));
+		e->last_verr = ratio;
+		if (acc[0]) {
+			e->n_pass2_calls++;
+			e->n_pass2_chunks += (long long)acc[0];
+		}
+		if (e->last_chunks > 1) e->adapt_halo(e->last_H, acc[0] > 0, ratio);
+		return GPT_OK;
+	};
 	for (int64_t s = 0; s < nsteps; s++) {
+		if (s > 0 && e->opt_adapt_every > 0 && s % e->opt_adapt_every == 0) {
+			int rc = adapt();
+			if (rc) return rc;
+		}
 		if (ms_per_step) {
 			if (flush_l2) CK(cudaMemsetAsync(flush.p, (int)(s & 0xff), flush_bytes, st));
 			CK(cudaEventRecord(ev[2 * s], st));
@@ -966,18 +993,9 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		for (auto &v : ev) cudaEventDestroy(v);
 		flush.release();
 	}
-	// verification verdicts accumulated on the device over this block of steps
-	if (e->d_acc.p && nsteps > 0) {
-		unsigned long long acc[2] = {0, 0};
-		CK(cudaMemcpy(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost));
-		double ratio;
-		memcpy(&ratio, &acc[1], sizeof(double));
-		e->last_verr = ratio;
-		if (acc[0]) {
-			e->n_pass2_calls++;
-			e->n_pass2_chunks += (long long)acc[0];
-		}
-		e->adapt_halo(e->last_H, acc[0] > 0, ratio);
+	if (nsteps > 0) {
+		int rc = adapt();
+		if (rc) return rc;
 	}
 	return GPT_OK;
 }

@@ -60,7 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 struct StarDev {
 	const double4 *samp;  // [N] {dt_ms, y, var, t_days}
 	const double *tdays;  // [N] compact copy of the sample times (transit window scan)
-	const unsigned char *tilereg;  // [ceil(N/TILE)] 1: every step of the tile is a regular-cadence step
+	const int *irr;       // sorted indices of the irregular steps (|dt - dt0| > dreg: gaps, the first sample)
+	int nirr;
+	int _pad2;
 	int N;
 	int _pad;
 	double dt0;    // base cadence (megaseconds)
@@ -898,7 +900,18 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		}
 	}
 	// block-uniform series order for regular steps: 1 (x <= 1e-8), 2 (x <= 5e-6), 0 = general loop
-	const int order = __syncthreads_or(xmax > 5.0e-6) ? 0 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1);
+	int order = __syncthreads_or(xmax > 5.0e-6) ? 0 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1);
+	if (st.nirr * 8 > st.N) order = 0;  // irregular sampling: the general loop
+	// cursor into the star's sorted list of irregular samples: first one after the start
+	int ip = 0;
+	{
+		int lo = 0, hi = st.nirr;
+		while (lo < hi) {
+			const int md = (lo + hi) >> 1;
+			if (st.irr[md] <= hs) lo = md + 1; else hi = md;
+		}
+		ip = lo;
+	}
 	const double *meanw = (TRANSIT && w < A.W) ? (A.mean + (size_t)gw * N) : nullptr;
 
 	// ---- state
@@ -998,9 +1011,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 			AC = sm.z + asum;
 		}
 
-		if (order != 0 && st.tilereg[tl]) {
-			// ---- fast loop: every step of this tile is a regular-cadence step.  Straight-line body:
-			// the dependent chain of step n and the preparation of step n+1 are independent.
+		if (order != 0) {
+			// ---- fast loop over the runs of regular-cadence steps of this tile.  Straight-line body: the
+			// dependent chain of step n and the preparation of step n+1 are independent.  The few
+			// irregular samples (gaps) are prepared one by one with the direct exp / sincos.
 			// model values of the next two samples, in flight
 			double mvN = load_mean(min(s0 + 1, s1 - 1)), mvNN = load_mean(min(s0 + 2, s1 - 1));
 			auto fast_range = [&](int a_, int b_, auto acc_tag, auto order_tag) {
@@ -1054,14 +1068,40 @@ GP_PRAGMA_UNROLL
 			using F = std::integral_constant<bool, false>;
 			using O1 = std::integral_constant<int, 1>;
 			using O2 = std::integral_constant<int, 2>;
-			if (order == 1) {
-				fast_range(s0, mid, F{}, O1{});
-				if (store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
-				fast_range(mid, s1, T{}, O1{});
-			} else {
-				fast_range(s0, mid, F{}, O2{});
-				if (store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
-				fast_range(mid, s1, T{}, O2{});
+			auto prepare_general = [&](int r) {
+				const double4 sm = tile[r];
+				const double x = sm.w * kDaysToMs;
+#pragma unroll
+				for (int k = 0; k < NT; k++) {
+					phiC[k] = exp(-K.c[k] * sm.x);
+					double sn_, cs_;
+					sincos(K.d[k] * x, &sn_, &cs_);
+					const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
+					VC[2 * k] = cs_;
+					VC[2 * k + 1] = sn_;
+					UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
+					UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
+				}
+				yC = residual(sm, r);
+				AC = sm.z + asum;
+			};
+			int a_ = s0;
+			while (a_ < s1) {
+				while (ip < st.nirr && st.irr[ip] <= a_) ip++;  // next irregular sample after a_
+				const int r = ip < st.nirr ? min(st.irr[ip], s1) : s1;
+				const int m1 = min(max(mid, a_), r);               // [a_, m1) halo, [m1, r) chunk proper
+				const bool store_now = store_here && a_ <= n0 && n0 < r;
+				if (order == 1) {
+					fast_range(a_, m1, F{}, O1{});
+					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+					fast_range(m1, r, T{}, O1{});
+				} else {
+					fast_range(a_, m1, F{}, O2{});
+					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+					fast_range(m1, r, T{}, O2{});
+				}
+				if (r < s1) prepare_general(r);
+				a_ = r;
 			}
 		} else {
 			// ---- general loop: gaps, irregular cadence, large timing jitter
