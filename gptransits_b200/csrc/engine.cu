@@ -55,6 +55,7 @@ struct Star {
 	double *tdays = nullptr;
 	int *irr = nullptr;
 	int nirr = 0;
+	double *tile_dt0 = nullptr;
 	int N = 0;
 	double dt0 = 0, dreg = 0, dmax = 0;
 	bool has_err = false;
@@ -185,6 +186,7 @@ static int sync_stars(gpt_engine *e)
 	for (size_t i = 0; i < h.size(); i++) {
 		h[i].samp = e->stars[i].samp;
 		h[i].tdays = e->stars[i].tdays;
+		h[i].tile_dt0 = e->stars[i].tile_dt0;
 		h[i].irr = e->stars[i].irr;
 		h[i].nirr = e->stars[i].nirr;
 		h[i]._pad2 = 0;
@@ -514,6 +516,7 @@ int gpt_star_clear(gpt_engine *e)
 		if (s.samp) cudaFree(s.samp);
 		if (s.tdays) cudaFree(s.tdays);
 		if (s.irr) cudaFree(s.irr);
+		if (s.tile_dt0) cudaFree(s.tile_dt0);
 	}
 	e->stars.clear();
 	e->stars_dirty = true;
@@ -731,6 +734,8 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	if (s.samp) cudaFree(s.samp);
 	if (s.tdays) cudaFree(s.tdays);
 	if (s.irr) cudaFree(s.irr);
+	if (s.tile_dt0) cudaFree(s.tile_dt0);
+	s.tile_dt0 = nullptr;
 	s.samp = nullptr;
 	s.tdays = nullptr;
 	s.irr = nullptr;
@@ -755,9 +760,22 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 		std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
 		dt0 = tmp[tmp.size() / 2];
 	}
+	// Regular steps are within 1e-3 of the median cadence.  Real timestamps drift slowly (barycentric
+	// correction, ~1e-4 relative over a season), so the series of the fast loop expand around a PER-TILE
+	// base cadence -- the first regular step of the tile -- and dmax is the largest within-tile deviation.
 	double dreg = 1e-3 * std::fabs(dt0), dmax = 0.0;
-	for (double dt : dts)
-		if (std::fabs(dt - dt0) <= dreg) dmax = std::max(dmax, std::fabs(dt - dt0));
+	const int64_t ntiles = (N + TILE - 1) / TILE;
+	std::vector<double> tile_dt0(ntiles, dt0);
+	for (int64_t tl = 0; tl < ntiles; tl++) {
+		const int64_t n_lo = tl * TILE, n_hi = std::min<int64_t>(N, n_lo + TILE);
+		for (int64_t n = n_lo; n < n_hi; n++)
+			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) {
+				tile_dt0[tl] = h[n].x;
+				break;
+			}
+		for (int64_t n = n_lo; n < n_hi; n++)
+			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) dmax = std::max(dmax, std::fabs(h[n].x - tile_dt0[tl]));
+	}
 	s.N = (int)N;
 	s.dt0 = dt0;
 	s.dreg = dreg;
@@ -770,6 +788,8 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 		for (int64_t n = 0; n < N; n++)
 			if (!(std::fabs(h[n].x - dt0) <= dreg)) irr.push_back((int)n);
 		s.nirr = (int)irr.size();
+		CK(cudaMalloc((void **)&s.tile_dt0, sizeof(double) * ntiles));
+		CK(cudaMemcpy(s.tile_dt0, tile_dt0.data(), sizeof(double) * ntiles, cudaMemcpyHostToDevice));
 		CK(cudaMalloc((void **)&s.irr, sizeof(int) * std::max<size_t>(1, irr.size())));
 		if (!irr.empty()) CK(cudaMemcpy(s.irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
 	}

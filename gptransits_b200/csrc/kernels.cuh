@@ -60,6 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 struct StarDev {
 	const double4 *samp;  // [N] {dt_ms, y, var, t_days}
 	const double *tdays;  // [N] compact copy of the sample times (transit window scan)
+	const double *tile_dt0;  // [ceil(N/TILE)] base cadence of each tile (timestamps drift: barycentric correction)
 	const int *irr;       // sorted indices of the irregular steps (|dt - dt0| > dreg: gaps, the first sample)
 	int nirr;
 	int _pad2;
@@ -899,8 +900,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 			K.sr0[k] = 0.0;
 		}
 	}
-	// block-uniform series order for regular steps: 1 (x <= 1e-8), 2 (x <= 5e-6), 0 = general loop
-	int order = __syncthreads_or(xmax > 5.0e-6) ? 0 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1);
+	// block-uniform series order for regular steps: 1 (x <= 1e-8), 2 (x <= 5e-6), 3 (x <= 2e-4), 0 = general loop
+	int order = __syncthreads_or(xmax > 2.0e-4) ? 0 : (__syncthreads_or(xmax > 5.0e-6) ? 3 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1));
 	if (st.nirr * 8 > st.N) order = 0;  // irregular sampling: the general loop
 	// cursor into the star's sorted list of irregular samples: first one after the start
 	int ip = 0;
@@ -981,6 +982,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		for (int i = 0; i < J; i++) dst[NP + i] = S.g[i];
 	};
 
+	double dt0_cur = st.dt0;
 	for (int tl = t_first; tl <= t_last; tl++) {
 		const int it = tl - t_first;
 		const int stg = it % NSTAGE;
@@ -990,6 +992,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		const int mid = min(max(n0, s0), s1);  // [s0, mid) halo, [mid, s1) chunk proper
 		const bool store_here = (!pass2 && c > 0 && active && n0 >= s0 && n0 < s1);
 
+		// per-tile base cadence: exp(-c dt0), cos/sin(d dt0) of THIS tile (recomputed only when it changes)
+		const double dt0t = st.tile_dt0[tl];
+		if (dt0t != dt0_cur) {
+			dt0_cur = dt0t;
+#pragma unroll
+			for (int k = 0; k < NT; k++) {
+				K.phi0[k] = exp(-K.c[k] * dt0t);
+				sincos(K.d[k] * dt0t, &K.sr0[k], &K.cr0[k]);
+			}
+		}
 		// anchor: exact rotation state at the first sample of the tile range
 		double phiC[NT], UC[J], VC[J], yC, AC;
 		{
@@ -1004,8 +1016,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 				VC[2 * k + 1] = sn_;
 				UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
 				UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
-				const double ddt = sm.x - st.dt0;
-				phiC[k] = (fabs(ddt) <= dreg) ? K.phi0[k] * exp_small_neg(K.c[k] * ddt) : exp(-K.c[k] * sm.x);
+				const double ddt = sm.x - dt0_cur;
+				phiC[k] = (fabs(sm.x - st.dt0) <= dreg) ? K.phi0[k] * exp_small_neg(K.c[k] * ddt) : exp(-K.c[k] * sm.x);
 			}
 			yC = residual(sm, s0);
 			AC = sm.z + asum;
@@ -1025,7 +1037,7 @@ GP_PRAGMA_UNROLL
 					const int m = min(n + 1, s1 - 1);
 					const double mv3 = load_mean(min(n + 3, s1 - 1));
 					const double4 sm = tile[m];
-					const double ddt = sm.x - st.dt0;
+					const double ddt = sm.x - dt0_cur;
 					double phiN[NT], UN[J], VN[J], yN, AN;
 					auto prepare = [&]() {
 #pragma unroll
@@ -1036,11 +1048,19 @@ GP_PRAGMA_UNROLL
 								phiN[k] = fma(-K.phi0[k], xc, K.phi0[k]);
 								cr = fma(-K.sr0[k], xd, K.cr0[k]);
 								sr = fma(K.cr0[k], xd, K.sr0[k]);
-							} else {
+							} else if (ORDER == 2) {
 								phiN[k] = K.phi0[k] * fma(fma(0.5, xc, -1.0), xc, 1.0);
 								const double h = fma(-0.5 * xd, xd, 1.0);
 								cr = fma(-K.sr0[k], xd, K.cr0[k] * h);
 								sr = fma(K.cr0[k], xd, K.sr0[k] * h);
+							} else {
+								// third order: |x| <= 2e-4 leaves x^4/24 < 1e-16
+								phiN[k] = K.phi0[k] * fma(fma(fma(-1.0 / 6.0, xc, 0.5), xc, -1.0), xc, 1.0);
+								const double x2 = xd * xd;
+								const double h = fma(-0.5, x2, 1.0);
+								const double s3 = xd * fma(-1.0 / 6.0, x2, 1.0);
+								cr = fma(-K.sr0[k], s3, K.cr0[k] * h);
+								sr = fma(K.cr0[k], s3, K.sr0[k] * h);
 							}
 							VN[2 * k] = fma(VC[2 * k], cr, -(VC[2 * k + 1] * sr));
 							VN[2 * k + 1] = fma(VC[2 * k + 1], cr, VC[2 * k] * sr);
@@ -1068,6 +1088,7 @@ GP_PRAGMA_UNROLL
 			using F = std::integral_constant<bool, false>;
 			using O1 = std::integral_constant<int, 1>;
 			using O2 = std::integral_constant<int, 2>;
+			using O3 = std::integral_constant<int, 3>;
 			auto prepare_general = [&](int r) {
 				const double4 sm = tile[r];
 				const double x = sm.w * kDaysToMs;
@@ -1095,10 +1116,14 @@ GP_PRAGMA_UNROLL
 					fast_range(a_, m1, F{}, O1{});
 					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
 					fast_range(m1, r, T{}, O1{});
-				} else {
+				} else if (order == 2) {
 					fast_range(a_, m1, F{}, O2{});
 					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
 					fast_range(m1, r, T{}, O2{});
+				} else {
+					fast_range(a_, m1, F{}, O3{});
+					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+					fast_range(m1, r, T{}, O3{});
 				}
 				if (r < s1) prepare_general(r);
 				a_ = r;
@@ -1113,8 +1138,8 @@ GP_PRAGMA_UNROLL
 					gp_step<NT, false>(S, phiC, UC, VC, yC, AC);
 				if (n + 1 < s1) {
 					const double4 sm = tile[n + 1];
-					const double ddt = sm.x - st.dt0;
-					if (fabs(ddt) <= dreg) {
+					const double ddt = sm.x - dt0_cur;
+					if (fabs(sm.x - st.dt0) <= dreg) {
 #pragma unroll
 						for (int k = 0; k < NT; k++) {
 							phiC[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);

@@ -55,9 +55,9 @@ def main():
     with np.load(os.path.join(ROOT, "tests", "golden", "example_lightcurves.npz")) as z:
         kic = (z["kic_time"], z["kic_flux"], z["kic_flux_err"])
         sim = (z["sim_time"], z["sim_flux"], z["sim_flux_err"])
-    res = [run("kic-012008916 (config 1: GP only, 24 walkers, 20000 steps as shipped)", KIC_CONFIG, *kic, 20000, 4000,
+    res = [run("kic-012008916 (config 1: GP only, 24 walkers, 20000 steps as shipped)", KIC_CONFIG, *kic, 20000, 20000,
                {"baseline": "remove"}),
-           run("sim-2452144 (config 2: GP + transit, 64 walkers)", SIM_CONFIG, sim[0], sim[1], None, 6000, 1500,
+           run("sim-2452144 (config 2: GP + transit, 64 walkers)", SIM_CONFIG, sim[0], sim[1], None, 6000, 6000,
                {"baseline": "remove", "inc_mapping": "cosi", "num_walkers": 64})]
     print(json.dumps(res, indent=1))
 
