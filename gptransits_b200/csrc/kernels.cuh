@@ -547,6 +547,8 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 // then applies the SAME per-sample test as the consumers to the few candidates, so the queue holds
 // exactly the samples for which the GP kernels will read mean[].  Walkers whose window covers
 // everything are swept by the whole CTA.
+constexpr int EPOCH_SCAN_CAP = 6144;  // items gathered per flush (24 KB of shared memory)
+
 __global__ void __launch_bounds__(TR_THREADS)
 transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
 			  unsigned int *qcount)
@@ -581,13 +583,63 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 	const double kminf = floor(fmin(ph0, ph1)) - 1.0, kmaxf = ceil(fmax(ph0, ph1)) + 1.0;
 	if (!(kmaxf - kminf < 2.0e9)) return;  // absurd period: no epoch bookkeeping possible; window tiny anyway
 	const long long kmin = (long long)kminf, kmax = (long long)kmaxf;
+	// The walker's items are gathered in shared memory and appended to the global queue with ONE
+	// atomic per flush (a single global counter cannot take tens of thousands of atomics per launch).
+	__shared__ unsigned int s_items[EPOCH_SCAN_CAP];
+	__shared__ unsigned int s_n, s_base;
+	if (threadIdx.x == 0) s_n = 0;
+	__syncthreads();
+	const long long nk = kmax - kmin + 1;
+	const long long rounds = (nk + blockDim.x - 1) / blockDim.x;
+	bool overflow = false;
+	for (long long rd = 0; rd < rounds; rd++) {
+		const long long k = kmin + rd * blockDim.x + threadIdx.x;
+		int a = 0, cnt = 0;
+		double hi = 0.0;
+		if (k <= kmax) {
+			const double tc = wcen + (double)k * pa;
+			const double half = whalf * pa;
+			const double eps = 1e-9 * pa + 1e-12 * fabs(tc);
+			const double lo = tc - half - eps;
+			hi = tc + half + eps;
+			if (!(hi < t[0] || lo > t[N - 1])) {
+				int b = N;  // first sample with t >= lo
+				while (a < b) {
+					const int mid = (a + b) >> 1;
+					if (t[mid] < lo) a = mid + 1; else b = mid;
+				}
+				for (int n = a; n < N && t[n] <= hi; n++) cnt += in_transit_window(t[n], wcen, inv_per, whalf) ? 1 : 0;
+			}
+		}
+		const unsigned int pos = cnt ? atomicAdd(&s_n, (unsigned int)cnt) : 0u;
+		const bool fits = pos + (unsigned int)cnt <= (unsigned int)EPOCH_SCAN_CAP;
+		if (cnt && fits) {
+			unsigned int q = pos;
+			for (int n = a; n < N && t[n] <= hi; n++)
+				if (in_transit_window(t[n], wcen, inv_per, whalf)) s_items[q++] = (unsigned int)n;
+		}
+		if (__syncthreads_or(cnt && !fits)) {
+			overflow = true;
+			break;
+		}
+	}
+	if (!overflow) {
+		__syncthreads();
+		const unsigned int have = s_n;
+		if (have == 0) return;
+		if (threadIdx.x == 0) s_base = atomicAdd(qcount, have);
+		__syncthreads();
+		for (unsigned int i = threadIdx.x; i < have; i += blockDim.x)
+			queue[s_base + i] = ((unsigned long long)(unsigned)gw << 32) | s_items[i];
+		return;
+	}
+	// overflow path: redo the walker, appending each epoch's items directly
 	for (long long k = kmin + threadIdx.x; k <= kmax; k += blockDim.x) {
 		const double tc = wcen + (double)k * pa;
 		const double half = whalf * pa;
 		const double eps = 1e-9 * pa + 1e-12 * fabs(tc);
 		const double lo = tc - half - eps, hi = tc + half + eps;
 		if (hi < t[0] || lo > t[N - 1]) continue;
-		// first sample with t >= lo
 		int a = 0, b = N;
 		while (a < b) {
 			const int mid = (a + b) >> 1;
