@@ -392,7 +392,7 @@ def run_ours(args):
         out = {
             "metric": "log-likelihood evals/s (walkers x steps)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": work["label"], "N": N, "walkers": W, "stars_per_gpu": nstars, "ndim": ndim, "J": J,
                        "evals_per_step": evals_per_step, "l2": "flushed between steps" if flush else "not flushed",
                        "sharding": "by star, no collective" if world > 1 else "single GPU",

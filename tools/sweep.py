@@ -26,9 +26,9 @@ def main():
     peak = eng.fp64_peak_tflops()
     print("fp64 peak", peak)
     ref = None
-    for cps in (1, 2):
-        for halo in (0, 128, 448):
-            eng.set_option("ctas_per_sm", cps)
+    for chunks in (148, 222, 296):
+        for halo in (320,):
+            eng.set_option("chunks", chunks)
             eng.set_option("halo", halo)
             eng.set_option("min_chunk_halos", 0.25)
             eng.log_prob(theta)
@@ -43,7 +43,7 @@ def main():
                 ref = lp
             err = np.max(np.abs(lp - ref) / np.abs(ref))
             fl = 254.0 * t.size * W
-            print(json.dumps({"ctas_per_sm": cps, "halo_opt": halo, "halo": eng.stat("halo"), "chunks": eng.stat("chunks"),
+            print(json.dumps({"chunks_opt": chunks, "halo_opt": halo, "halo": eng.stat("halo"), "chunks": eng.stat("chunks"),
                               "L": eng.stat("chunk_len"), "ms_total": float(np.median(ms)), "kern_ms": k,
                               "chunk_frac": fl / (k["chunk"] * 1e-3) / 1e12 / peak,
                               "pass2_new": eng.stat("pass2_chunks") - p2, "ratio": eng.stat("verify_ratio"),
