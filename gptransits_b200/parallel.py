@@ -109,11 +109,13 @@ class HalfEnsembleSampler:
         import torch
         sizes = [walker_slice(n, r, self.world) for r in range(self.world)]
         width = max(h - l for l, h in sizes)
-        buf = torch.zeros(width, dtype=torch.float64)
-        buf[:hi - lo] = torch.from_numpy(mine)
-        out = [torch.zeros(width, dtype=torch.float64) for _ in range(self.world)]
+        # NCCL (NVLink) moves device tensors; gloo (the CPU tests) host tensors
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else "cpu"
+        buf = torch.zeros(width, dtype=torch.float64, device=dev)
+        buf[:hi - lo] = torch.from_numpy(mine).to(dev)
+        out = [torch.zeros(width, dtype=torch.float64, device=dev) for _ in range(self.world)]
         self.dist.all_gather(out, buf)
-        return np.concatenate([o[:h - l].numpy() for o, (l, h) in zip(out, sizes)])
+        return np.concatenate([o[:h - l].cpu().numpy() for o, (l, h) in zip(out, sizes)])
 
     def step_once(self):
         W, H = self.W, self.W // 2
