@@ -380,9 +380,14 @@ def run_ours(args):
         import oracle
         oracle.build()
         cores = os.cpu_count() or 1
-        nsample = args.cpu_evals or min(W, max(2 * cores, 32))
-        v, dt = cpu_evals_per_s(spec, t, ys[0], work["yerr"], th[:nsample], cores)
-        v1, dt1 = cpu_evals_per_s(spec, t, ys[0], work["yerr"], th[:max(2, nsample // cores)], 1)
+        # bounded sample: a pilot sizes it to about 8 s of wall time on all cores (theta rows are reused)
+        pilot = th[:max(cores, 8)]
+        vp, _ = cpu_evals_per_s(spec, t, ys[0], work["yerr"], pilot, cores)
+        nsample = args.cpu_evals or int(min(max(8.0 * vp, 2 * cores), 200000))
+        rows = np.resize(np.arange(th.shape[0]), nsample)
+        v, dt = cpu_evals_per_s(spec, t, ys[0], work["yerr"], th[rows], cores)
+        n1 = max(2, min(nsample // cores, int(2.0 * vp / cores) + 2))
+        v1, dt1 = cpu_evals_per_s(spec, t, ys[0], work["yerr"], th[rows[:n1]], 1)
         cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
                "sample": f"{nsample} posterior evaluations of star 0 of this workload in {dt:.2f} s on {cores} threads; "
                          f"single thread: {v1:.2f} evals/s",

@@ -181,3 +181,19 @@ def test_half_ensemble_sampler_equals_oracle_sampler(kic_lc, kic_config):
     chain, logp = HalfEnsembleSampler(fn, init, seed=5).run(6)
     ochain, ologp, _ = oracle.sample(spec, t[sel], y, yerr, init, 6, seed=5)
     assert np.array_equal(chain, ochain) and np.array_equal(logp, ologp)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on the small C2 workload."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "c2",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert key in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
