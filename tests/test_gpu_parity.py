@@ -541,3 +541,40 @@ def test_device_gelman_rubin_matches_host(engine, kic_lc, kic_config):
     engine.sampler_end()
     want, _, _ = convergence.gelman_rubin(chain[0][:, 40:120, :])
     assert rel(rhat[0], want) < 1e-10
+
+
+def test_eccentric_and_odd_transit_parameters_through_the_posterior(engine):
+    """Free e and w (Kepler solve + eccentric in-transit window) and parameter corners that normal
+    priors allow (negative period, a < 1, planet larger than the star, inclination past 90 degrees):
+    the sparse transit path feeding the GP must agree with the oracle, not just gpt_transit_flux."""
+    t, y, yerr = synthetic_star(3000, 31)
+    tr_cfg = {"params": {"values": {
+        "P": [False, None, "normal", 5.9, 2.0], "t0": [False, None, "normal", 3.0, 1.0],
+        "Rrat": [False, None, "normal", 0.1, 0.3], "aR": [False, None, "normal", 8.0, 4.0],
+        "cosi": [False, None, "normal", 88.0, 3.0],
+        "e": [False, None, "uniform", 0.0, 0.7], "w": [False, None, "uniform", 0.0, 360.0],
+        "u1": [False, None, "uniform", 0.0, 1.0], "u2": [False, None, "uniform", 0.0, 0.5]}}}
+    np.random.seed(17)
+    gp = GPModel(C3_CONFIG_GP[:2] + C3_CONFIG_GP[3:])
+    tr = BatmanModel(tr_cfg)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    theta = np.hstack([gp.sample_prior(40), tr.sample_prior(40)])
+    k = gp.ndim
+    theta[0, k:k + 5] = [-4.0, 3.0, 0.1, 8.0, 88.0]     # negative period
+    theta[1, k:k + 5] = [5.9, 3.0, 0.1, 0.8, 88.0]      # a < 1
+    theta[2, k:k + 5] = [5.9, 3.0, 1.3, 3.0, 85.0]      # planet larger than the star
+    theta[3, k:k + 5] = [5.9, 3.0, 0.1, 8.0, 93.0]      # inclination past 90
+    theta[4, k:k + 5] = [5.9, 3.0, -0.1, 8.0, 88.0]     # negative radius ratio (batman takes |rp|)
+    theta[5, k + 5] = 0.0                                # exactly circular with free w
+    theta[6, k + 5] = 5e-6                               # batman's e < 1e-5 shortcut
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    for chunks in (1, 4, 0):
+        engine.set_option("chunks", chunks)
+        lp, parts = engine.log_prob(theta, return_parts=True)
+        assert_parts_close(parts, want)
+    engine.set_option("chunks", 0)
+    assert np.isfinite(want_lp).sum() >= 30
