@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="size of the bounded CPU sample")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine option (gpt_set_option), e.g. --opt pdl=0; recorded in config")
     ap.add_argument("--batch-walkers", type=int, default=2048,
                     help="size of the extra resident log_prob batch (0 = skip)")
     return ap.parse_args()
@@ -271,6 +273,9 @@ def run_ours(args):
     np.random.seed(args.seed + rank)
     gp, tr, spec = model_of(work, t)
     eng = Engine(local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, float(v))
     ys = inject_transit(eng, work, spec)
     nstars = len(ys)
     for s, y in enumerate(ys):
@@ -401,7 +406,8 @@ def run_ours(args):
             "config": {"workload": work["label"], "N": N, "walkers": W, "stars_per_gpu": nstars, "ndim": ndim, "J": J,
                        "evals_per_step": evals_per_step, "l2": "flushed between steps" if flush else "not flushed",
                        "sharding": "by star, no collective" if world > 1 else "single GPU",
-                       "chunks": stats["chunks"], "chunk_len": stats["chunk_len"], "halo": stats["halo"]},
+                       "chunks": stats["chunks"], "chunk_len": stats["chunk_len"], "halo": stats["halo"],
+                       **({"engine_options": args.opt} if args.opt else {})},
             "sampler_steps_per_s": args.steps / (total_ms * 1e-3),
             "acceptance_fraction": float(nacc.mean() / (max(3, args.warmup) + 2 * args.steps)),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

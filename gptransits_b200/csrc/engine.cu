@@ -51,13 +51,15 @@ struct DevBuf {
 };
 
 struct Star {
+	char *blob = nullptr;     // one allocation per star (samp | tdays | tile_dt0 | irr), reused by re-uploads that fit
+	size_t blob_cap = 0;
 	double4 *samp = nullptr;
 	double *tdays = nullptr;
 	int *irr = nullptr;
 	int nirr = 0;
 	double *tile_dt0 = nullptr;
 	int N = 0;
-	double dt0 = 0, dreg = 0, dmax = 0;
+	double dt0 = 0, dreg = 0, dmax = 0, cdev = 0;
 	bool has_err = false;
 };
 
@@ -82,6 +84,9 @@ struct gpt_engine {
 	int opt_epoch_scan = 1;
 	int opt_adapt_every = 32;  // sampler steps between halo adaptations
 	int opt_transit_strict = 0;
+	int opt_series_order_min = 0;
+	int opt_speculate = 1;
+	long long n_spec_replays = 0;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
 	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
@@ -102,6 +107,8 @@ struct gpt_engine {
 	DevBuf<unsigned int> d_qcount;
 	DevBuf<int> d_nbad;      // [1]
 	DevBuf<double> d_verr;   // [1]
+	char *h_stage = nullptr;  // pinned staging buffer of gpt_star_upload (grow-only)
+	size_t h_stage_cap = 0;
 	int *h_nbad = nullptr;   // pinned
 	double *h_verr = nullptr;
 
@@ -114,6 +121,8 @@ struct gpt_engine {
 	DevBuf<double> s_x, s_lpx, s_q, s_lq, s_fac, s_chain, s_logp;
 	DevBuf<int> s_act, s_ids;
 	DevBuf<long long> s_nacc;
+	DevBuf<double> s_snap_x, s_snap_lpx;  // ensemble at the start of a speculative block
+	DevBuf<long long> s_snap_nacc;
 
 	// running totals written by the finalize kernel: [0] flagged chunks, [1] max error ratio (bits)
 	DevBuf<unsigned long long> d_acc;
@@ -195,6 +204,7 @@ static int sync_stars(gpt_engine *e)
 		h[i].dt0 = e->stars[i].dt0;
 		h[i].dreg = e->stars[i].dreg;
 		h[i].dmax = e->stars[i].dmax;
+		h[i].cdev = e->stars[i].cdev;
 	}
 	CK(e->d_stars.ensure(std::max<size_t>(1, h.size())));
 	if (!h.empty())
@@ -278,6 +288,34 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 	if (nchunks == 1) H = 0;
 }
 
+// Launch with programmatic stream serialisation (see pdl_wait in kernels.cuh): the kernel may become resident
+// while its predecessor in the stream is still running and blocks in griddepcontrol.wait until that one
+// has completed.  Off by default (option "pdl"): measured on the C3 sampler step it gains nothing (0.669 ms
+// per step with, 0.652 ms without) -- the stream's back-to-back launch gaps are already short and the
+// early-resident CTAs cost more than the hidden prologues save.
+static int g_pdl = 0;
+template <typename... KArgs, typename... Args>
+static void launch_kx(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = (g_pdl && pdl) ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+	launch_kx(true, kernel, grid, block, smem, st, std::forward<Args>(args)...);
+}
+
 // flux of the queued (walker, sample) items; "transit_strict" selects batman's own operation order
 static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *stars, int W, int ss, double exp_time,
 				int mode, const double *prep, const unsigned long long *queue, const unsigned int *qcount,
@@ -285,21 +323,36 @@ static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *s
 {
 	const int grid = 148 * 2 * TR_MINBLOCKS;
 	if (e->opt_transit_strict)
-		transit_eval_kernel<true><<<grid, TR_THREADS, 0, st>>>(stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+		launch_k(transit_eval_kernel<true>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
 	else
-		transit_eval_kernel<false><<<grid, TR_THREADS, 0, st>>>(stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+		launch_k(transit_eval_kernel<false>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
 }
 
 // threads per chunk CTA: one per walker of the star, a whole number of warps, at most 128
 static int chunk_threads(int W) { return std::min(CHUNK_THREADS, ((W + 31) / 32) * 32); }
 
+static void launch_finalize(int nt, int nwalk, cudaStream_t st, const FinalArgs &f)
+{
+	switch (nt) {
+	case 1: launch_k(gp_finalize_kernel<1>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 2: launch_k(gp_finalize_kernel<2>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 3: launch_k(gp_finalize_kernel<3>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 4: launch_k(gp_finalize_kernel<4>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	default: break;
+	}
+}
+
 template <int NT>
 static void launch_chunk_nt(bool transit, dim3 grid, int threads, cudaStream_t st, const ChunkArgs &a)
 {
+	// Pass 1 is launched stream-ordered: CTAs of a programmatic launch are placed as the preceding kernel
+	// frees resources, which can put two chunk CTAs on one SM and none on another -- with a grid of one
+	// CTA per SM that doubles the kernel's duration.  Pass 2 (normally an immediate exit) overlaps.
+	const bool pdl = a.pass2 != 0;
 	if (transit)
-		gp_chunk_kernel<NT, true><<<grid, threads, 0, st>>>(a);
+		launch_kx(pdl, gp_chunk_kernel<NT, true>, dim3(grid), dim3(threads), 0, st, a);
 	else
-		gp_chunk_kernel<NT, false><<<grid, threads, 0, st>>>(a);
+		launch_kx(pdl, gp_chunk_kernel<NT, false>, dim3(grid), dim3(threads), 0, st, a);
 }
 
 static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStream_t st, const ChunkArgs &a)
@@ -318,7 +371,7 @@ static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStrea
 // is always enqueued (it exits immediately when nothing was flagged) so the sequence is graph-safe.
 static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
 			double *d_parts, bool host_sync, const PrepPropose *propose = nullptr,
-			const FinalAccept *accept = nullptr, bool *accept_done = nullptr)
+			const FinalAccept *accept = nullptr, bool *accept_done = nullptr, bool speculative = false)
 {
 	if (accept_done) *accept_done = false;
 	int rc = check_stars(e, star0, nstars);
@@ -355,9 +408,9 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	memset(&pr, 0, sizeof(pr));
 	if (propose) pr = *propose;
 	if (nwalk <= 4096)
-		prep_kernel<<<nwalk, PREP_THREADS, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
+		launch_k(prep_kernel, dim3(nwalk), dim3(PREP_THREADS), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
 	else
-		prep_wide_kernel<<<(nwalk + 63) / 64, 64, 0, st>>>(m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
+		launch_k(prep_wide_kernel, dim3((nwalk + 63) / 64), dim3(64), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
 	e->timer_end(TK_PREP);
 	e->n_launch++;
 	if (m.has_transit) {
@@ -369,10 +422,10 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			// one thread per transit epoch: a few per 256 samples at most for any realistic period
 			int et = 32;
 			while (et < TR_THREADS && et * 256 < N) et *= 2;
-			transit_epoch_scan_kernel<<<nwalk, et, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p);
+			launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p);
 		}
 		else
-			transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
+			launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 								      e->d_mean.p, 0);
 		e->timer_end(TK_TRSCAN);
 		launch_transit_eval(e, st, dst, W, m.supersample, m.exp_time, m.ellip_mode,
@@ -387,7 +440,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
 		a.lp = d_lp; a.parts = d_parts; a.W = W; a.nwalk = nwalk; a.N = N;
 		a.gp = m.ncomp > 0; a.transit = m.has_transit; a.has_err = e->stars[star0].has_err;
-		diag_kernel<<<(nwalk * 32 + 255) / 256, 256, 0, st>>>(a);
+		launch_k(diag_kernel, dim3((nwalk * 32 + 255) / 256), dim3(256), 0, st, a);
 		e->n_launch++;
 		CK(cudaGetLastError());
 		return GPT_OK;
@@ -410,6 +463,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
 	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p;
 	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
+	a.min_order = e->opt_series_order_min;
 	const int cthreads = chunk_threads(W);
 	dim3 grid(nchunks, (W + cthreads - 1) / cthreads, nstars);
 	e->timer_begin(TK_CHUNK);
@@ -434,7 +488,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		if (accept_done) *accept_done = true;
 	}
 	e->timer_begin(TK_FINAL);
-	gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
+	launch_finalize(nt, nwalk, st, f);
 	e->timer_end(TK_FINAL);
 	e->n_launch++;
 
@@ -443,11 +497,13 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		g.stars = dst; g.prep = e->d_prep.p; g.flags = e->d_flags.p; g.mean = e->d_mean.p;
 		g.lp = d_lp; g.parts = d_parts; g.W = W; g.nwalk = nwalk; g.N = N; g.nterms = nt;
 		g.transit = m.has_transit;
-		gp_generic_kernel<<<(nwalk + 31) / 32, 32, 0, st>>>(g);
+		launch_k(gp_generic_kernel, dim3((nwalk + 31) / 32), dim3(32), 0, st, g);
 		e->n_launch++;
 	}
 
-	if (f.verify) {
+	// speculative: the caller (the sampler) checks the accumulated verdicts once per block of steps and
+	// replays the block with pass 2 when a chunk was flagged, so nothing is enqueued here
+	if (f.verify && !speculative) {
 		bool need = true;
 		if (host_sync) {
 			CK(cudaMemcpyAsync(e->h_nbad, e->d_nbad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -469,7 +525,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			launch_chunk(nt, m.has_transit != 0, grid, cthreads, st, a);
 			f.verify = 0;
 			f.skip_if_clean = 1;
-			gp_finalize_kernel<<<nwalk, FIN_THREADS, 0, st>>>(f);
+			launch_finalize(nt, nwalk, st, f);
 			e->timer_end(TK_PASS2);
 			e->n_launch += 2;
 		}
@@ -512,12 +568,8 @@ int gpt_star_clear(gpt_engine *e)
 	if (!e) return GPT_E_INVALID;
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
-	for (auto &s : e->stars) {
-		if (s.samp) cudaFree(s.samp);
-		if (s.tdays) cudaFree(s.tdays);
-		if (s.irr) cudaFree(s.irr);
-		if (s.tile_dt0) cudaFree(s.tile_dt0);
-	}
+	for (auto &s : e->stars)
+		if (s.blob) cudaFree(s.blob);
 	e->stars.clear();
 	e->stars_dirty = true;
 	return GPT_OK;
@@ -536,6 +588,8 @@ void gpt_engine_destroy(gpt_engine *e)
 	e->d_queue.release(); e->d_qcount.release(); e->d_wbad.release();
 	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
 	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
+	e->s_snap_x.release(); e->s_snap_lpx.release(); e->s_snap_nacc.release();
+	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_nbad) cudaFreeHost(e->h_nbad);
 	if (e->h_verr) cudaFreeHost(e->h_verr);
 	cudaStreamDestroy(e->stream);
@@ -560,6 +614,12 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_min_chunk_halos = value;
 	} else if (k == "transit_strict") {
 		e->opt_transit_strict = value != 0;
+	} else if (k == "series_order_min") {
+		e->opt_series_order_min = std::min(4, std::max(0, (int)value));
+	} else if (k == "speculate") {
+		e->opt_speculate = value != 0;
+	} else if (k == "pdl") {
+		g_pdl = value != 0;
 	} else if (k == "adapt_every") {
 		e->opt_adapt_every = (int)value;
 	} else if (k == "epoch_scan") {
@@ -593,6 +653,7 @@ int gpt_get_stat(gpt_engine *e, const char *key, double *value)
 	if (k == "launches") *value = (double)e->n_launch;
 	else if (k == "pass2_calls") *value = (double)e->n_pass2_calls;
 	else if (k == "pass2_chunks") *value = (double)e->n_pass2_chunks;
+	else if (k == "spec_replays") *value = (double)e->n_spec_replays;
 	else if (k == "evals") *value = (double)e->n_evals;
 	else if (k == "verify_ratio") *value = e->last_verr;
 	else if (k == "chunks") *value = e->last_chunks;
@@ -731,15 +792,23 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	if ((size_t)star >= e->stars.size()) e->stars.resize(star + 1);
 	Star &s = e->stars[star];
 	CK(cudaStreamSynchronize(e->stream));
-	if (s.samp) cudaFree(s.samp);
-	if (s.tdays) cudaFree(s.tdays);
-	if (s.irr) cudaFree(s.irr);
-	if (s.tile_dt0) cudaFree(s.tile_dt0);
-	s.tile_dt0 = nullptr;
-	s.samp = nullptr;
-	s.tdays = nullptr;
-	s.irr = nullptr;
-	std::vector<double4> h(N);
+	// layout of the star's blob; everything is assembled in pinned host memory and sent with one copy
+	const int64_t ntiles = (N + TILE - 1) / TILE;
+	const size_t off_samp = 0, off_tdays = sizeof(double4) * (size_t)N, off_tile = off_tdays + sizeof(double) * (size_t)N;
+	const size_t off_irr = off_tile + sizeof(double) * (size_t)ntiles;
+	const size_t stage_need = off_irr + sizeof(int) * ((size_t)N + 1);  // irr can hold every sample
+	if (e->h_stage_cap < stage_need) {
+		if (e->h_stage) cudaFreeHost(e->h_stage);
+		e->h_stage = nullptr;
+		e->h_stage_cap = 0;
+		CK(cudaMallocHost((void **)&e->h_stage, stage_need + stage_need / 8));
+		e->h_stage_cap = stage_need + stage_need / 8;
+	}
+	double4 *h = reinterpret_cast<double4 *>(e->h_stage + off_samp);
+	double *h_tdays = reinterpret_cast<double *>(e->h_stage + off_tdays);
+	double *tile_dt0 = reinterpret_cast<double *>(e->h_stage + off_tile);
+	int *h_irr = reinterpret_cast<int *>(e->h_stage + off_irr);
+	memcpy(h_tdays, t_days, sizeof(double) * (size_t)N);
 	std::vector<double> dts;
 	dts.reserve(N);
 	double xprev = 0.0;
@@ -756,45 +825,64 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	}
 	double dt0 = 0.0;
 	if (!dts.empty()) {
-		std::vector<double> tmp(dts);
-		std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
-		dt0 = tmp[tmp.size() / 2];
+		std::nth_element(dts.begin(), dts.begin() + dts.size() / 2, dts.end());
+		dt0 = dts[dts.size() / 2];
 	}
 	// Regular steps are within 1e-3 of the median cadence.  Real timestamps drift slowly (barycentric
 	// correction, ~1e-4 relative over a season), so the series of the fast loop expand around a PER-TILE
-	// base cadence -- the first regular step of the tile -- and dmax is the largest within-tile deviation.
-	double dreg = 1e-3 * std::fabs(dt0), dmax = 0.0;
-	const int64_t ntiles = (N + TILE - 1) / TILE;
-	std::vector<double> tile_dt0(ntiles, dt0);
+	// base cadence -- the mean regular step of the tile -- and dmax is the largest within-tile deviation.
+	// cdev is the largest accumulated deviation |sum (dt_n - tile_dt0)| any run of regular steps inside a
+	// tile can build up (range of the running sum, restarted at irregular samples): when max(c, d) * cdev
+	// is negligible the loop advances by the tile's constant cadence and ignores the per-step deviation.
+	double dreg = 1e-3 * std::fabs(dt0), dmax = 0.0, cdev = 0.0;
+	for (int64_t tl = 0; tl < ntiles; tl++) tile_dt0[tl] = dt0;
 	for (int64_t tl = 0; tl < ntiles; tl++) {
 		const int64_t n_lo = tl * TILE, n_hi = std::min<int64_t>(N, n_lo + TILE);
-		for (int64_t n = n_lo; n < n_hi; n++)
-			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) {
-				tile_dt0[tl] = h[n].x;
-				break;
+		double sum = 0.0;
+		int64_t cnt = 0;
+		for (int64_t n = std::max<int64_t>(n_lo, 1); n < n_hi; n++)
+			if (std::fabs(h[n].x - dt0) <= dreg) {
+				sum += h[n].x - dt0;
+				cnt++;
 			}
-		for (int64_t n = n_lo; n < n_hi; n++)
-			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) dmax = std::max(dmax, std::fabs(h[n].x - tile_dt0[tl]));
+		if (cnt) tile_dt0[tl] = dt0 + sum / (double)cnt;
+		double run = 0.0, lo = 0.0, hi = 0.0;
+		for (int64_t n = n_lo; n < n_hi; n++) {
+			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) {
+				dmax = std::max(dmax, std::fabs(h[n].x - tile_dt0[tl]));
+				run += h[n].x - tile_dt0[tl];
+				lo = std::min(lo, run);
+				hi = std::max(hi, run);
+				cdev = std::max(cdev, hi - lo);
+			} else {
+				run = lo = hi = 0.0;
+			}
+		}
 	}
 	s.N = (int)N;
 	s.dt0 = dt0;
 	s.dreg = dreg;
 	s.dmax = dmax;
+	s.cdev = cdev;
 	s.has_err = yerr != nullptr;
-	CK(cudaMalloc((void **)&s.samp, sizeof(double4) * N));
-	CK(cudaMemcpy(s.samp, h.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
-	{
-		std::vector<int> irr;
-		for (int64_t n = 0; n < N; n++)
-			if (!(std::fabs(h[n].x - dt0) <= dreg)) irr.push_back((int)n);
-		s.nirr = (int)irr.size();
-		CK(cudaMalloc((void **)&s.tile_dt0, sizeof(double) * ntiles));
-		CK(cudaMemcpy(s.tile_dt0, tile_dt0.data(), sizeof(double) * ntiles, cudaMemcpyHostToDevice));
-		CK(cudaMalloc((void **)&s.irr, sizeof(int) * std::max<size_t>(1, irr.size())));
-		if (!irr.empty()) CK(cudaMemcpy(s.irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
+	int nirr = 0;
+	for (int64_t n = 0; n < N; n++)
+		if (!(std::fabs(h[n].x - dt0) <= dreg)) h_irr[nirr++] = (int)n;
+	s.nirr = nirr;
+	const size_t total = off_irr + sizeof(int) * (size_t)std::max(1, nirr);
+	if (s.blob_cap < total) {
+		if (s.blob) cudaFree(s.blob);
+		s.blob = nullptr;
+		s.blob_cap = 0;
+		CK(cudaMalloc((void **)&s.blob, total));
+		s.blob_cap = total;
 	}
-	CK(cudaMalloc((void **)&s.tdays, sizeof(double) * N));
-	CK(cudaMemcpy(s.tdays, t_days, sizeof(double) * N, cudaMemcpyHostToDevice));
+	s.samp = reinterpret_cast<double4 *>(s.blob + off_samp);
+	s.tdays = reinterpret_cast<double *>(s.blob + off_tdays);
+	s.tile_dt0 = reinterpret_cast<double *>(s.blob + off_tile);
+	s.irr = reinterpret_cast<int *>(s.blob + off_irr);
+	CK(cudaMemcpyAsync(s.blob, e->h_stage, total, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
 	e->stars_dirty = true;
 	return GPT_OK;
 }
@@ -861,7 +949,7 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 	prep_transit_direct_kernel<<<(W + 127) / 128, 128, 0, e->stream>>>(e->model.exp_time, e->d_theta.p, W, e->d_prep.p,
 									    e->d_flags.p);
 	dim3 g(W, (N + TR_THREADS - 1) / TR_THREADS);
-	transit_scan_kernel<<<g, TR_THREADS, 0, e->stream>>>(e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
+	launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, e->stream, e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
 							     e->d_qcount.p, e->d_mean.p, 1);
 	launch_transit_eval(e, e->stream, e->d_stars.p + star, W, e->model.supersample,
 								   e->model.exp_time, e->model.ellip_mode, e->d_prep.p,
@@ -954,7 +1042,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
 	// verification verdicts accumulate on the device; every "adapt_every" steps (and at the end) they
 	// are read back -- one small synchronisation -- to steer the halo length
-	auto adapt = [&]() -> int {
+	auto adapt = [&](bool *flagged) -> int {
 		unsigned long long acc[2] = {0, 0};
 		CK(cudaMemcpyAsync(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
@@ -962,60 +1050,106 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		double ratio;
 		memcpy(&ratio, &acc[1], sizeof(double));
 		e->last_verr = ratio;
-		if (acc[0]) {
+		if (flagged) *flagged = acc[0] > 0;
+		if (acc[0] && !flagged) {
 			e->n_pass2_calls++;
 			e->n_pass2_chunks += (long long)acc[0];
 		}
 		if (e->last_chunks > 1) e->adapt_halo(e->last_H, acc[0] > 0, ratio);
 		return GPT_OK;
 	};
-	for (int64_t s = 0; s < nsteps; s++) {
-		if (s > 0 && e->opt_adapt_every > 0 && s % e->opt_adapt_every == 0) {
-			int rc = adapt();
-			if (rc) return rc;
-		}
-		if (ms_per_step) {
-			if (flush_l2) CK(cudaMemsetAsync(flush.p, (int)(s & 0xff), flush_bytes, st));
-			CK(cudaEventRecord(ev[2 * s], st));
-		}
-		sampler_split_kernel<<<ns, 256, (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st>>>(S, e->s_step);
-		e->n_launch++;
-		for (int half = 0; half < 2; half++) {
-			PrepPropose pr;
-			pr.enabled = 1;
-			pr.half = half;
-			pr.step = e->s_step;
-			pr.S = S;
-			FinalAccept ac;
-			ac.enabled = 1;
-			ac.half = half;
-			ac.step = e->s_step;
-			ac.slot = keep ? e->s_kept : -1LL;
-			ac.S = S;
-			bool fused = false;
-			int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false, &pr, &ac, &fused);
-			if (rc) return rc;
-			if (!fused) {
-				sampler_accept_kernel<<<(nh + 127) / 128, 128, 0, st>>>(S, e->s_step, half, ac.slot);
-				e->n_launch++;
+	auto run_steps = [&](int64_t sa, int64_t sb, bool speculative) -> int {
+		for (int64_t s = sa; s < sb; s++) {
+			if (ms_per_step) {
+				if (flush_l2) CK(cudaMemsetAsync(flush.p, (int)(s & 0xff), flush_bytes, st));
+				CK(cudaEventRecord(ev[2 * s], st));
 			}
+			launch_k(sampler_split_kernel, dim3(ns), dim3(256), (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st, S, e->s_step);
+			e->n_launch++;
+			for (int half = 0; half < 2; half++) {
+				PrepPropose pr;
+				pr.enabled = 1;
+				pr.half = half;
+				pr.step = e->s_step;
+				pr.S = S;
+				FinalAccept ac;
+				ac.enabled = 1;
+				ac.half = half;
+				ac.step = e->s_step;
+				ac.slot = keep ? e->s_kept : -1LL;
+				ac.S = S;
+				bool fused = false;
+				int rc = eval_enqueue(e, e->s_star0, ns, S.q, H, S.lq, nullptr, false, &pr, &ac, &fused, speculative);
+				if (rc) return rc;
+				if (!fused) {
+					launch_k(sampler_accept_kernel, dim3((nh + 127) / 128), dim3(128), 0, st, S, e->s_step, half, ac.slot);
+					e->n_launch++;
+				}
+			}
+			if (keep) e->s_kept++;
+			if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
+			e->s_step++;
 		}
-		if (keep) e->s_kept++;
-		if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
-		e->s_step++;
+		CK(cudaGetLastError());
+		return GPT_OK;
+	};
+	auto add_times = [&](int64_t sa, int64_t sb) -> int {
+		if (!ms_per_step) return GPT_OK;
+		for (int64_t s = sa; s < sb; s++) {
+			float t = 0.f;
+			CK(cudaEventElapsedTime(&t, ev[2 * s], ev[2 * s + 1]));
+			ms_per_step[s] += t;
+		}
+		return GPT_OK;
+	};
+	if (ms_per_step)
+		for (int64_t s = 0; s < nsteps; s++) ms_per_step[s] = 0.f;
+	// Blocks of "adapt_every" steps.  A block runs speculatively: no repair pass is enqueued, the chunk
+	// verification only accumulates its verdicts on the device.  They are read once per block (one small
+	// synchronisation, also used to steer the halo); if any chunk was flagged the ensemble is rolled back
+	// to the start of the block and the block is replayed with the repair pass -- the RNG is counter
+	// based, so the replay reproduces the same moves and the result does not depend on the speculation.
+	const bool can_speculate = e->opt_speculate && !e->may_generic && e->opt_verify;
+	const int64_t block = e->opt_adapt_every > 0 ? e->opt_adapt_every : 64;
+	const size_t nw = (size_t)ns * W;
+	for (int64_t sa = 0; sa < nsteps; sa += block) {
+		const int64_t sb = std::min<int64_t>(nsteps, sa + block);
+		const unsigned long long step_at = e->s_step;
+		const long long kept_at = e->s_kept;
+		if (can_speculate) {
+			CK(e->s_snap_x.ensure(nw * ndim));
+			CK(e->s_snap_lpx.ensure(nw));
+			CK(e->s_snap_nacc.ensure(nw));
+			CK(cudaMemcpyAsync(e->s_snap_x.p, S.x, nw * ndim * sizeof(double), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(e->s_snap_lpx.p, S.lpx, nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(e->s_snap_nacc.p, S.nacc, nw * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+		}
+		int rc = run_steps(sa, sb, can_speculate);
+		if (rc) return rc;
+		bool flagged = false;
+		rc = adapt(can_speculate ? &flagged : nullptr);
+		if (rc) return rc;
+		rc = add_times(sa, sb);
+		if (rc) return rc;
+		if (can_speculate && flagged) {
+			e->n_spec_replays++;
+			CK(cudaMemcpyAsync(S.x, e->s_snap_x.p, nw * ndim * sizeof(double), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(S.lpx, e->s_snap_lpx.p, nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(S.nacc, e->s_snap_nacc.p, nw * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+			e->s_step = step_at;
+			e->s_kept = kept_at;
+			rc = run_steps(sa, sb, false);
+			if (rc) return rc;
+			rc = adapt(nullptr);
+			if (rc) return rc;
+			rc = add_times(sa, sb);
+			if (rc) return rc;
+		}
 	}
-	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
 	if (ms_per_step) {
-		for (int64_t s = 0; s < nsteps; s++) {
-			CK(cudaEventElapsedTime(&ms_per_step[s], ev[2 * s], ev[2 * s + 1]));
-		}
 		for (auto &v : ev) cudaEventDestroy(v);
 		flush.release();
-	}
-	if (nsteps > 0) {
-		int rc = adapt();
-		if (rc) return rc;
 	}
 	return GPT_OK;
 }
@@ -1205,11 +1339,11 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 		reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
 		PrepPropose pr;
 		memset(&pr, 0, sizeof(pr));
-		prep_kernel<<<1, PREP_THREADS, 0, st>>>(m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
+		launch_k(prep_kernel, dim3(1), dim3(PREP_THREADS), 0, st, m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
 	}
 	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);
-		transit_scan_kernel<<<g, TR_THREADS, 0, st>>>(dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
+		launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
 							      e->d_mean.p, 0);
 		launch_transit_eval(e, st, dst, 1, m.supersample, m.exp_time, m.ellip_mode,
 										e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);

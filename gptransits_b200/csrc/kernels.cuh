@@ -56,6 +56,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		: "memory");
 }
 
+// Programmatic dependent launch (sm_90+).  Every kernel of the evaluation / sampler sequence is launched
+// with programmatic stream serialisation and follows one discipline: [prologue] -> pdl_wait() -> pdl_trigger()
+// -> body.  The wait returns when the preceding kernel has completed and flushed; because the trigger comes
+// after the wait, the NEXT kernel can only become resident once the PREVIOUS one has completed, so a prologue
+// may read anything written two or more kernels back (never the immediate predecessor's output) and must not
+// write.  Launch latency and prologues overlap the tail of the preceding kernel.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_trigger()
+{
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ device-side descriptors
 struct StarDev {
 	const double4 *samp;  // [N] {dt_ms, y, var, t_days}
@@ -68,7 +84,8 @@ struct StarDev {
 	int _pad;
 	double dt0;    // base cadence (megaseconds)
 	double dreg;   // |dt - dt0| <= dreg: "regular" step (series for exp / rotation)
-	double dmax;   // max |dt - dt0| over regular steps
+	double dmax;   // max |dt - tile_dt0| over regular steps
+	double cdev;   // max accumulated |sum (dt - tile_dt0)| over a run of regular steps inside a tile
 };
 
 // packed symmetric index (i <= j) for a J x J matrix
@@ -200,6 +217,8 @@ __global__ void __launch_bounds__(PREP_THREADS)
 prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep, int *flags,
 	    PrepReset R, PrepPropose PR)
 {
+	pdl_wait();
+	pdl_trigger();
 	__shared__ double s_th[MAX_NDIM];
 	__shared__ double s_lp[2];
 	__shared__ double s_gp[4];  // asum, jit2, maxcd, typemask
@@ -352,6 +371,8 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 __global__ void prep_wide_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep,
 			    int *flags, PrepReset R, PrepPropose PR)
 {
+	pdl_wait();
+	pdl_trigger();
 	int gw = blockIdx.x * blockDim.x + threadIdx.x;
 	if (gw == 0) {
 		if (R.nbad) *R.nbad = 0;
@@ -516,6 +537,8 @@ __global__ void __launch_bounds__(TR_THREADS)
 transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
 		    unsigned int *qcount, double *out, int dense)
 {
+	pdl_wait();
+	pdl_trigger();
 	const int gw = blockIdx.x;   // walkers on x (up to 2^31 - 1 blocks), sample blocks on y
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
@@ -553,6 +576,8 @@ __global__ void __launch_bounds__(TR_THREADS)
 transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
 			  unsigned int *qcount)
 {
+	pdl_wait();
+	pdl_trigger();
 	const int gw = blockIdx.x;
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
@@ -664,6 +689,8 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS)
 transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep,
 		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense)
 {
+	pdl_wait();
+	pdl_trigger();
 	if (ss < 1) ss = 1;
 	const unsigned int nitems = *qcount;
 	const int lane = threadIdx.x & 31;
@@ -736,6 +763,7 @@ struct ChunkArgs {
 	int W;                    // walkers per star
 	int N, nchunks, L, H;
 	int pass2;
+	int min_order;            // lowest treatment of regular steps the fast loop may use (option series_order_min)
 };
 
 // exp(-x) for |x| <= 1e-3, full double accuracy
@@ -873,11 +901,147 @@ __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], 
 	}
 }
 
-// per-walker constants of the fast loop
+// The same step on the SCALED state of the fast loop.  Inside a run of regular-cadence steps anchored at
+// sample a (scale 1 there) the thread keeps  P^ = P / (s s^T),  g^ = g / s,  s_i = exp(-c_i (x_n - x_a)),
+// and is handed  U~ = s o U  and  V~ = V / s.  Then S = phi phi^T o P needs no arithmetic at all
+// (S / (s' s'^T) = P^ with s' = s o phi) and every quantity of the step keeps its form:
+//   t^ = P^ U~     D = A - U~.t^     z = y - U~.g^     P^ += (V~ - t^)(V~ - t^)^T / D     g^ += (V~ - t^) z / D
+// D and z are the physical (unscaled) values, so quad / log-det accumulate as before.  The callers unscale at
+// the end of a run (<= 128 steps; shorter when a walker's c dt0 is large, so s^2 stays far from underflow).
+template <int NT, bool ACC, typename Mid = NoMid>
+__device__ __forceinline__ void gp_step_scaled(GPCore<NT> &S, const double (&U)[2 * NT], const double (&V)[2 * NT],
+					       double y, double Avar, Mid mid = Mid())
+{
+	constexpr int J = 2 * NT;
+	double tv[J], acc0[J], acc1[J];
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+		acc0[i] = 0.0;
+		acc1[i] = 0.0;
+	}
+#pragma unroll
+	for (int j = 0; j < J; j += 2) {
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double s0_ = (i <= j) ? S.P[tri(i, j, J)] : S.P[tri(j, i, J)];
+			acc0[i] = fma(s0_, U[j], acc0[i]);
+		}
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double s1_ = (i <= j + 1) ? S.P[tri(i, j + 1, J)] : S.P[tri(j + 1, i, J)];
+			acc1[i] = fma(s1_, U[j + 1], acc1[i]);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < J; i++) tv[i] = acc0[i] + acc1[i];
+	double utp[NT], zpp[NT];
+#pragma unroll
+	for (int k = 0; k < NT; k++) {
+		utp[k] = fma(U[2 * k], tv[2 * k], U[2 * k + 1] * tv[2 * k + 1]);
+		zpp[k] = fma(U[2 * k], S.g[2 * k], U[2 * k + 1] * S.g[2 * k + 1]);
+	}
+	double ut = utp[0], zp = zpp[0];
+#pragma unroll
+	for (int k = 1; k < NT; k++) {
+		ut += utp[k];
+		zp += zpp[k];
+	}
+	const double D = Avar - ut;
+	const double z = y - zp;
+	S.notpd |= !(D > 0.0);
+	const double invD = fast_rcp(D);
+	double vt[J], wv[J];
+#pragma unroll
+	for (int i = 0; i < J; i++) vt[i] = V[i] - tv[i];
+	mid();
+#pragma unroll
+	for (int i = 0; i < J; i++) wv[i] = vt[i] * invD;
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+#pragma unroll
+		for (int j = i; j < J; j++) S.P[tri(i, j, J)] = fma(vt[i], wv[j], S.P[tri(i, j, J)]);
+		S.g[i] = fma(wv[i], z, S.g[i]);
+	}
+	if (ACC) {
+		double zi = z * invD;
+		S.quad = fma(z, zi, S.quad);
+		S.zmax = fmax(S.zmax, fabs(zi));
+		S.dmin = fmin(S.dmin, D);
+		S.ldm *= D;
+		int hi = __double2hiint(S.ldm);
+		int ex = ((hi >> 20) & 0x7ff) - 1023;
+		S.lde += ex;
+		S.ldm = __hiloint2double(hi - (ex << 20), __double2loint(S.ldm));
+	}
+}
+
+// per-walker constants of the fast loop: damped / anti-damped rotation by one base-cadence step,
+//   (cu, su) = exp(-c dt0) (cos, sin)(d dt0)   advances U~,     (cv, sv) = exp(+c dt0) (cos, sin)(d dt0)   advances V~
 template <int NT>
 struct FastCoef {
-	double c[NT], d[NT], phi0[NT], cr0[NT], sr0[NT];  // exp(-c dt0), cos(d dt0), sin(d dt0)
+	double c[NT], d[NT], cu[NT], su[NT], cv[NT], sv[NT];
+	__device__ __forceinline__ void set_base(double dt)
+	{
+#pragma unroll
+		for (int k = 0; k < NT; k++) {
+			const double ph = exp(-c[k] * dt), ri = exp(c[k] * dt);
+			double sn_, cs_;
+			sincos(d[k] * dt, &sn_, &cs_);
+			cu[k] = ph * cs_;
+			su[k] = ph * sn_;
+			cv[k] = ri * cs_;
+			sv[k] = ri * sn_;
+		}
+	}
 };
+
+// U~, V~ of the next sample from those of the current one.  ORDER 0: the step is the tile's base cadence
+// (constant coefficients); ORDER 1..3: series in the deviation ddt = dt - dt0 of this step
+// (|c ddt|, |d ddt| <= 1e-8, 5e-6, 2e-4: the neglected terms are below 1e-16).
+template <int NT, int ORDER>
+__device__ __forceinline__ void fast_advance(const FastCoef<NT> &K, double ddt, const double (&UC)[2 * NT],
+					     const double (&VC)[2 * NT], double (&UN)[2 * NT], double (&VN)[2 * NT])
+{
+#pragma unroll
+	for (int k = 0; k < NT; k++) {
+		double cu, su, cv, sv;
+		if (ORDER == 0) {
+			cu = K.cu[k];
+			su = K.su[k];
+			cv = K.cv[k];
+			sv = K.sv[k];
+		} else if (ORDER == 1) {
+			const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
+			cu = fma(-K.su[k], xd, fma(-K.cu[k], xc, K.cu[k]));
+			su = fma(K.cu[k], xd, fma(-K.su[k], xc, K.su[k]));
+			cv = fma(-K.sv[k], xd, fma(K.cv[k], xc, K.cv[k]));
+			sv = fma(K.cv[k], xd, fma(K.sv[k], xc, K.sv[k]));
+		} else {
+			const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
+			double e, ei, c1, s1;
+			if (ORDER == 2) {
+				e = fma(fma(0.5, xc, -1.0), xc, 1.0);
+				ei = fma(fma(0.5, xc, 1.0), xc, 1.0);
+				c1 = fma(-0.5 * xd, xd, 1.0);
+				s1 = xd;
+			} else {
+				e = fma(fma(fma(-1.0 / 6.0, xc, 0.5), xc, -1.0), xc, 1.0);
+				ei = fma(fma(fma(1.0 / 6.0, xc, 0.5), xc, 1.0), xc, 1.0);
+				const double x2 = xd * xd;
+				c1 = fma(-0.5, x2, 1.0);
+				s1 = xd * fma(-1.0 / 6.0, x2, 1.0);
+			}
+			cu = e * fma(-K.su[k], s1, K.cu[k] * c1);
+			su = e * fma(K.cu[k], s1, K.su[k] * c1);
+			cv = ei * fma(-K.sv[k], s1, K.cv[k] * c1);
+			sv = ei * fma(K.cv[k], s1, K.sv[k] * c1);
+		}
+		UN[2 * k] = fma(UC[2 * k], cu, -(UC[2 * k + 1] * su));
+		UN[2 * k + 1] = fma(UC[2 * k + 1], cu, UC[2 * k] * su);
+		VN[2 * k] = fma(VC[2 * k], cv, -(VC[2 * k + 1] * sv));
+		VN[2 * k + 1] = fma(VC[2 * k + 1], cv, VC[2 * k] * sv);
+	}
+}
 
 #ifndef GP_UNROLL
 #define GP_UNROLL 2
@@ -907,7 +1071,13 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	const int n0 = c * A.L;
 	const int n1 = min(N, n0 + A.L);
 	const bool pass2 = A.pass2 != 0;
-	if (pass2 && *A.nbad == 0) return;
+	if (pass2 || !TRANSIT) {
+		// pass 2: the verdict comes from the finalize kernel right before this launch; without a transit
+		// model the prep kernel is the immediate predecessor
+		pdl_wait();
+		pdl_trigger();
+		if (pass2 && *A.nbad == 0) return;
+	}
 	const int hs = pass2 ? n0 : max(0, n0 - A.H);
 
 	int fl = 0;
@@ -925,36 +1095,44 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	FastCoef<NT> K;
 	double asum = 1.0;
 	double wcen = 0.0, inv_per = 1.0, whalf = -1.0;  // inactive threads: never in window
-	double dreg = -1.0;                             // |ddt| <= dreg: series for exp / rotation
 	double xmax = 0.0;                              // max |c ddt|, |d ddt| on regular steps
+	double xdev = 0.0;                              // max |c|, |d| times the accumulated deviation of a run
+	double cdt = 0.0;                               // max c dt0: decay of the scale over one step
+#pragma unroll
+	for (int k = 0; k < NT; k++) K.c[k] = K.d[k] = 0.0;
 	if (active) {
 		asum = pp[PP_ASUM];
 #pragma unroll
 		for (int k = 0; k < NT; k++) {
 			K.c[k] = pp[PP_TERMS + 4 * k + 2];
 			K.d[k] = pp[PP_TERMS + 4 * k + 3];
-			K.phi0[k] = exp(-K.c[k] * st.dt0);
-			sincos(K.d[k] * st.dt0, &K.sr0[k], &K.cr0[k]);
+			cdt = fmax(cdt, fabs(K.c[k]));
 		}
+		cdt *= 1.002 * fabs(st.dt0);
 		if (TRANSIT) {
 			wcen = pp[PP_WCEN];
 			inv_per = pp[PP_INVPER];
 			whalf = pp[PP_WHALF];
 		}
-		if (!(fl & WF_SLOWTRIG)) dreg = st.dreg;
 		xmax = (fl & WF_SLOWTRIG) ? 1.0 : pp[PP_MAXCD] * st.dmax;
-	} else {
-#pragma unroll
-		for (int k = 0; k < NT; k++) {
-			K.c[k] = K.d[k] = 0.0;
-			K.phi0[k] = 1.0;
-			K.cr0[k] = 1.0;
-			K.sr0[k] = 0.0;
-		}
+		xdev = pp[PP_MAXCD] * st.cdev;
 	}
-	// block-uniform series order for regular steps: 1 (x <= 1e-8), 2 (x <= 5e-6), 3 (x <= 2e-4), 0 = general loop
-	int order = __syncthreads_or(xmax > 2.0e-4) ? 0 : (__syncthreads_or(xmax > 5.0e-6) ? 3 : (__syncthreads_or(xmax > 1.0e-8) ? 2 : 1));
-	if (st.nirr * 8 > st.N) order = 0;  // irregular sampling: the general loop
+	// block-uniform treatment of the regular steps: 0 = constant cadence (accumulated deviation negligible),
+	// 1..3 = series order in the per-step deviation (x <= 1e-8, 5e-6, 2e-4), 4 = general loop
+	int order;
+	if (__syncthreads_or(xmax > 2.0e-4) || st.nirr * 8 > st.N) order = 4;
+	else if (__syncthreads_or(xmax > 5.0e-6)) order = 3;
+	else if (__syncthreads_or(xmax > 1.0e-8)) order = 2;
+	else if (__syncthreads_or(xdev > 1.0e-10)) order = 1;
+	else order = 0;
+	order = max(order, A.min_order);
+	// run length between re-anchorings: the scale s = exp(-c (x - x_anchor)) must keep s^2 above ~1e-260
+	int runlen = TILE;
+	if (order < 4) {
+		while (runlen >= 8 && __syncthreads_or(cdt * runlen > 300.0)) runlen >>= 1;
+		if (runlen < 8) order = 4;
+	}
+	if (order < 4) K.set_base(st.dt0);
 	// cursor into the star's sorted list of irregular samples: first one after the start
 	int ip = 0;
 	{
@@ -1005,6 +1183,12 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	if (threadIdx.x == 0) {
 		for (int tl = t_first; tl <= t_last && tl < t_first + NSTAGE; tl++) issue(tl);
 	}
+	// everything above read only the star and the prep kernel's output (three launches back): the transit
+	// model of the preceding kernel is needed from here on, and nothing was written yet
+	if (!pass2 && TRANSIT) {
+		pdl_wait();
+		pdl_trigger();
+	}
 	if (TRANSIT && meanw) {
 		prefetch_l1(meanw + hs);
 		prefetch_l1(meanw + min(hs + 16, N - 1));
@@ -1041,26 +1225,23 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		mbar_wait(&s_bar[stg], (uint32_t)((it / NSTAGE) & 1));
 		const int s0 = max(tl * TILE, hs), s1 = min((tl + 1) * TILE, n1);
 		const double4 *tile = &s_tile[stg][0] - tl * TILE;
-		const int mid = min(max(n0, s0), s1);  // [s0, mid) halo, [mid, s1) chunk proper
 		const bool store_here = (!pass2 && c > 0 && active && n0 >= s0 && n0 < s1);
+		double *const cdst = A.carryE + ((size_t)gw * A.nchunks + c) * CS;
 
-		// per-tile base cadence: exp(-c dt0), cos/sin(d dt0) of THIS tile (recomputed only when it changes)
+		// per-tile base cadence (recomputed only when it changes)
 		const double dt0t = st.tile_dt0[tl];
 		if (dt0t != dt0_cur) {
 			dt0_cur = dt0t;
-#pragma unroll
-			for (int k = 0; k < NT; k++) {
-				K.phi0[k] = exp(-K.c[k] * dt0t);
-				sincos(K.d[k] * dt0t, &K.sr0[k], &K.cr0[k]);
-			}
+			if (order < 4) K.set_base(dt0t);
 		}
-		// anchor: exact rotation state at the first sample of the tile range
+		// exact inputs of sample r: phi = exp(-c dt), U, V from sincos(d x)
 		double phiC[NT], UC[J], VC[J], yC, AC;
-		{
-			const double4 sm = tile[s0];
+		auto prepare_general = [&](int r) {
+			const double4 sm = tile[r];
 			const double x = sm.w * kDaysToMs;
 #pragma unroll
 			for (int k = 0; k < NT; k++) {
+				phiC[k] = exp(-K.c[k] * sm.x);
 				double sn_, cs_;
 				sincos(K.d[k] * x, &sn_, &cs_);
 				const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
@@ -1068,17 +1249,18 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 				VC[2 * k + 1] = sn_;
 				UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
 				UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
-				const double ddt = sm.x - dt0_cur;
-				phiC[k] = (fabs(sm.x - st.dt0) <= dreg) ? K.phi0[k] * exp_small_neg(K.c[k] * ddt) : exp(-K.c[k] * sm.x);
 			}
-			yC = residual(sm, s0);
+			yC = residual(sm, r);
 			AC = sm.z + asum;
-		}
+		};
+		prepare_general(s0);
 
-		if (order != 0) {
-			// ---- fast loop over the runs of regular-cadence steps of this tile.  Straight-line body: the
-			// dependent chain of step n and the preparation of step n+1 are independent.  The few
-			// irregular samples (gaps) are prepared one by one with the direct exp / sincos.
+		if (order < 4) {
+			// ---- fast loop over runs of regular-cadence steps.  A run starts with one exact step on the
+			// unscaled state (tile start, the sample after a gap, or a re-anchoring point); the following
+			// steps run on the scaled state (gp_step_scaled) with a straight-line body in which the
+			// dependent chain of step n and the preparation of step n+1 are independent; the state is
+			// unscaled again at the end of the run.
 			// model values of the next two samples, in flight
 			double mvN = load_mean(min(s0 + 1, s1 - 1)), mvNN = load_mean(min(s0 + 2, s1 - 1));
 			auto fast_range = [&](int a_, int b_, auto acc_tag, auto order_tag) {
@@ -1090,43 +1272,15 @@ GP_PRAGMA_UNROLL
 					const double mv3 = load_mean(min(n + 3, s1 - 1));
 					const double4 sm = tile[m];
 					const double ddt = sm.x - dt0_cur;
-					double phiN[NT], UN[J], VN[J], yN, AN;
+					double UN[J], VN[J], yN, AN;
 					auto prepare = [&]() {
-#pragma unroll
-						for (int k = 0; k < NT; k++) {
-							const double xc = K.c[k] * ddt, xd = K.d[k] * ddt;
-							double cr, sr;
-							if (ORDER == 1) {
-								phiN[k] = fma(-K.phi0[k], xc, K.phi0[k]);
-								cr = fma(-K.sr0[k], xd, K.cr0[k]);
-								sr = fma(K.cr0[k], xd, K.sr0[k]);
-							} else if (ORDER == 2) {
-								phiN[k] = K.phi0[k] * fma(fma(0.5, xc, -1.0), xc, 1.0);
-								const double h = fma(-0.5 * xd, xd, 1.0);
-								cr = fma(-K.sr0[k], xd, K.cr0[k] * h);
-								sr = fma(K.cr0[k], xd, K.sr0[k] * h);
-							} else {
-								// third order: |x| <= 2e-4 leaves x^4/24 < 1e-16
-								phiN[k] = K.phi0[k] * fma(fma(fma(-1.0 / 6.0, xc, 0.5), xc, -1.0), xc, 1.0);
-								const double x2 = xd * xd;
-								const double h = fma(-0.5, x2, 1.0);
-								const double s3 = xd * fma(-1.0 / 6.0, x2, 1.0);
-								cr = fma(-K.sr0[k], s3, K.cr0[k] * h);
-								sr = fma(K.cr0[k], s3, K.sr0[k] * h);
-							}
-							VN[2 * k] = fma(VC[2 * k], cr, -(VC[2 * k + 1] * sr));
-							VN[2 * k + 1] = fma(VC[2 * k + 1], cr, VC[2 * k] * sr);
-							UN[2 * k] = fma(UC[2 * k], cr, -(UC[2 * k + 1] * sr));
-							UN[2 * k + 1] = fma(UC[2 * k + 1], cr, UC[2 * k] * sr);
-						}
+						fast_advance<NT, ORDER>(K, ddt, UC, VC, UN, VN);
 						yN = residual_mv(sm, mvN);
 						AN = sm.z + asum;
 					};
-					gp_step<NT, ACC>(S, phiC, UC, VC, yC, AC, prepare);
+					gp_step_scaled<NT, ACC>(S, UC, VC, yC, AC, prepare);
 					mvN = mvNN;
 					mvNN = mv3;
-#pragma unroll
-					for (int k = 0; k < NT; k++) phiC[k] = phiN[k];
 #pragma unroll
 					for (int i = 0; i < J; i++) {
 						UC[i] = UN[i];
@@ -1138,52 +1292,94 @@ GP_PRAGMA_UNROLL
 			};
 			using T = std::integral_constant<bool, true>;
 			using F = std::integral_constant<bool, false>;
-			using O1 = std::integral_constant<int, 1>;
-			using O2 = std::integral_constant<int, 2>;
-			using O3 = std::integral_constant<int, 3>;
-			auto prepare_general = [&](int r) {
-				const double4 sm = tile[r];
-				const double x = sm.w * kDaysToMs;
-#pragma unroll
-				for (int k = 0; k < NT; k++) {
-					phiC[k] = exp(-K.c[k] * sm.x);
-					double sn_, cs_;
-					sincos(K.d[k] * x, &sn_, &cs_);
-					const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
-					VC[2 * k] = cs_;
-					VC[2 * k + 1] = sn_;
-					UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
-					UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
+			auto run_fast = [&](int a_, int b_, auto acc_tag) {
+				if (order == 0) fast_range(a_, b_, acc_tag, std::integral_constant<int, 0>{});
+				else if (order == 1) fast_range(a_, b_, acc_tag, std::integral_constant<int, 1>{});
+				else if (order == 2) fast_range(a_, b_, acc_tag, std::integral_constant<int, 2>{});
+				else fast_range(a_, b_, acc_tag, std::integral_constant<int, 3>{});
+			};
+			// exact step of sample a_ (accumulating iff acc), then U~, V~ of sample a_+1 at scale 1
+			auto first_step = [&](int a_, bool acc) {
+				const int m = min(a_ + 1, s1 - 1);
+				const double mv3 = load_mean(min(a_ + 3, s1 - 1));
+				const double4 sm = tile[m];
+				const double ddt = sm.x - dt0_cur;
+				const double q0 = S.quad, l0 = S.ldm, z0 = S.zmax, d0 = S.dmin;
+				const int e0 = S.lde;
+				gp_step<NT, true>(S, phiC, UC, VC, yC, AC);
+				if (!acc) {
+					S.quad = q0;
+					S.ldm = l0;
+					S.zmax = z0;
+					S.dmin = d0;
+					S.lde = e0;
 				}
-				yC = residual(sm, r);
+				double UN[J], VN[J];
+				if (order == 0) fast_advance<NT, 0>(K, ddt, UC, VC, UN, VN);
+				else if (order == 1) fast_advance<NT, 1>(K, ddt, UC, VC, UN, VN);
+				else if (order == 2) fast_advance<NT, 2>(K, ddt, UC, VC, UN, VN);
+				else fast_advance<NT, 3>(K, ddt, UC, VC, UN, VN);
+				yC = residual_mv(sm, mvN);
 				AC = sm.z + asum;
+				mvN = mvNN;
+				mvNN = mv3;
+#pragma unroll
+				for (int i = 0; i < J; i++) {
+					UC[i] = UN[i];
+					VC[i] = VN[i];
+				}
+			};
+			// scale of the state after sample `last` of the run anchored at a_
+			auto scale_of = [&](int a_, int last, double (&sc)[NT]) {
+				const double span = (tile[last].w - tile[a_].w) * kDaysToMs;
+#pragma unroll
+				for (int k = 0; k < NT; k++) sc[k] = exp(-K.c[k] * span);
 			};
 			int a_ = s0;
 			while (a_ < s1) {
 				while (ip < st.nirr && st.irr[ip] <= a_) ip++;  // next irregular sample after a_
-				const int r = ip < st.nirr ? min(st.irr[ip], s1) : s1;
-				const int m1 = min(max(mid, a_), r);               // [a_, m1) halo, [m1, r) chunk proper
+				int r = ip < st.nirr ? min(st.irr[ip], s1) : s1;
+				r = min(r, a_ + runlen);
 				const bool store_now = store_here && a_ <= n0 && n0 < r;
-				if (order == 1) {
-					fast_range(a_, m1, F{}, O1{});
-					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
-					fast_range(m1, r, T{}, O1{});
-				} else if (order == 2) {
-					fast_range(a_, m1, F{}, O2{});
-					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
-					fast_range(m1, r, T{}, O2{});
-				} else {
-					fast_range(a_, m1, F{}, O3{});
-					if (store_now) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
-					fast_range(m1, r, T{}, O3{});
+				if (store_now && n0 == a_) store_carry(cdst);
+				first_step(a_, a_ >= n0);
+				if (a_ + 1 < r) {
+					const int m1 = min(max(n0, a_ + 1), r);  // [a_+1, m1) halo, [m1, r) chunk proper
+					run_fast(a_ + 1, m1, F{});
+					if (store_now && n0 > a_) {
+						double sc[NT];
+						scale_of(a_, n0 - 1, sc);
+#pragma unroll
+						for (int i = 0; i < J; i++) {
+#pragma unroll
+							for (int j = i; j < J; j++) cdst[tri(i, j, J)] = S.P[tri(i, j, J)] * (sc[i / 2] * sc[j / 2]);
+							cdst[NP + i] = S.g[i] * sc[i / 2];
+						}
+					}
+					run_fast(m1, r, T{});
+					double sc[NT];
+					scale_of(a_, r - 1, sc);
+#pragma unroll
+					for (int i = 0; i < J; i++) {
+#pragma unroll
+						for (int j = i; j < J; j++) S.P[tri(i, j, J)] *= sc[i / 2] * sc[j / 2];
+						S.g[i] *= sc[i / 2];
+					}
 				}
 				if (r < s1) prepare_general(r);
 				a_ = r;
 			}
 		} else {
-			// ---- general loop: gaps, irregular cadence, large timing jitter
+			// ---- general loop: irregular cadence, large timing jitter, very fast decay
+			const double dreg = (fl & WF_SLOWTRIG) ? -1.0 : st.dreg;
+			double phi0[NT], cr0[NT], sr0[NT];
+#pragma unroll
+			for (int k = 0; k < NT; k++) {
+				phi0[k] = exp(-K.c[k] * dt0_cur);
+				sincos(K.d[k] * dt0_cur, &sr0[k], &cr0[k]);
+			}
 			for (int n = s0; n < s1; n++) {
-				if (n == n0 && store_here) store_carry(A.carryE + ((size_t)gw * A.nchunks + c) * CS);
+				if (n == n0 && store_here) store_carry(cdst);
 				if (n >= n0)
 					gp_step<NT, true>(S, phiC, UC, VC, yC, AC);
 				else
@@ -1191,36 +1387,25 @@ GP_PRAGMA_UNROLL
 				if (n + 1 < s1) {
 					const double4 sm = tile[n + 1];
 					const double ddt = sm.x - dt0_cur;
-					if (fabs(sm.x - st.dt0) <= dreg) {
+					if (active && fabs(sm.x - st.dt0) <= dreg) {
 #pragma unroll
 						for (int k = 0; k < NT; k++) {
-							phiC[k] = K.phi0[k] * exp_small_neg(K.c[k] * ddt);
+							phiC[k] = phi0[k] * exp_small_neg(K.c[k] * ddt);
 							double s1_, c1_;
 							sincos_small(K.d[k] * ddt, s1_, c1_);
-							const double cr = K.cr0[k] * c1_ - K.sr0[k] * s1_;
-							const double sr = K.sr0[k] * c1_ + K.cr0[k] * s1_;
+							const double cr = cr0[k] * c1_ - sr0[k] * s1_;
+							const double sr = sr0[k] * c1_ + cr0[k] * s1_;
 							const double v0 = VC[2 * k], v1 = VC[2 * k + 1], u0 = UC[2 * k], u1 = UC[2 * k + 1];
 							VC[2 * k] = fma(v0, cr, -(v1 * sr));
 							VC[2 * k + 1] = fma(v1, cr, v0 * sr);
 							UC[2 * k] = fma(u0, cr, -(u1 * sr));
 							UC[2 * k + 1] = fma(u1, cr, u0 * sr);
 						}
+						yC = residual(sm, n + 1);
+						AC = sm.z + asum;
 					} else {
-						const double x = sm.w * kDaysToMs;
-#pragma unroll
-						for (int k = 0; k < NT; k++) {
-							phiC[k] = exp(-K.c[k] * sm.x);
-							double sn_, cs_;
-							sincos(K.d[k] * x, &sn_, &cs_);
-							const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
-							VC[2 * k] = cs_;
-							VC[2 * k + 1] = sn_;
-							UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
-							UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
-						}
+						prepare_general(n + 1);
 					}
-					yC = residual(sm, n + 1);
-					AC = sm.z + asum;
 				}
 			}
 		}
@@ -1264,9 +1449,12 @@ struct FinalArgs {
 	FinalAccept AC;
 };
 
-// One block of FIN_THREADS per walker; threads stride over chunks / chunk boundaries; the sums use a
-// fixed-shape shared-memory + warp-shuffle tree, so they are deterministic.
-constexpr int FIN_THREADS = 128;
+// One block of FIN_THREADS per walker; one thread per chunk / chunk boundary (strided beyond FIN_THREADS
+// chunks) with the carry size known at compile time, so a thread's 2 x CS carry loads are all in flight at
+// once; the sums use a fixed-shape shared-memory + warp-shuffle tree, so they are deterministic.  In the
+// sampler the last warp prepares the accept/reject of the walker (RNG, current row, proposal row) while the
+// others reduce, and commits it -- one lane per dimension -- as soon as the log-probability is known.
+constexpr int FIN_THREADS = 160;
 
 __device__ __forceinline__ double block_sum(double v, double *scratch)
 {
@@ -1282,19 +1470,88 @@ __device__ __forceinline__ double block_sum(double v, double *scratch)
 	return t;
 }
 
+// warp-cooperative form of sampler_accept_one: everything that does not depend on the new log-probability
+struct AcceptPre {
+	size_t gwk;
+	int w;
+	double logu, lpw, fac;
+	double q[2], x[2];  // dimensions lane, lane + 32
+};
+__device__ __forceinline__ void sampler_accept_prefetch(const SamplerDev &S, unsigned long long step, int half, int gi,
+							int lane, AcceptPre &P)
+{
+	const int H = S.W / 2;
+	const int star = gi / H, i = gi - star * H;
+	const uint32_t sid = (uint32_t)S.star_ids[star];
+	P.w = S.act[((size_t)star * 2 + half) * H + i];
+	uint32_t r[4];
+	rng_words(S.seed, sid, step, (uint32_t)P.w, 1, r);
+	P.logu = log(u53(r[2], r[3]));
+	P.gwk = (size_t)star * S.W + P.w;
+	P.lpw = S.lpx[P.gwk];
+	P.fac = S.fac[gi];
+#pragma unroll
+	for (int k = 0; k < 2; k++) {
+		const int d = lane + 32 * k;
+		P.q[k] = d < S.ndim ? S.q[(size_t)gi * S.ndim + d] : 0.0;
+		P.x[k] = d < S.ndim ? S.x[P.gwk * S.ndim + d] : 0.0;
+	}
+}
+__device__ __forceinline__ void sampler_accept_commit(const SamplerDev &S, const AcceptPre &P, int gi, double lq,
+						      long long slot, int lane)
+{
+	const int H = S.W / 2;
+	const int star = gi / H;
+	const double lnpdiff = P.fac + lq - P.lpw;
+	const bool acc = lnpdiff > P.logu;
+	double *xs = S.x + P.gwk * S.ndim;
+	double *c = slot >= 0 ? S.chain + (P.gwk * S.cap + slot) * S.ndim : nullptr;
+#pragma unroll
+	for (int k = 0; k < 2; k++) {
+		const int d = lane + 32 * k;
+		if (d < S.ndim) {
+			const double v = acc ? P.q[k] : P.x[k];
+			if (acc) xs[d] = v;
+			if (c) c[d] = v;
+		}
+	}
+	for (int d = lane + 64; d < S.ndim; d += 32) {
+		const double v = acc ? S.q[(size_t)gi * S.ndim + d] : xs[d];
+		if (acc) xs[d] = v;
+		if (c) c[d] = v;
+	}
+	if (lane == 0) {
+		if (acc) {
+			S.lpx[P.gwk] = lq;
+			S.nacc[P.gwk] += 1;
+		}
+		if (slot >= 0) S.logp[((size_t)star * S.cap + slot) * S.W + P.w] = acc ? lq : P.lpw;
+	}
+}
+
+template <int NT>
 __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 {
+	constexpr int J = 2 * NT, NP = J * (J + 1) / 2, CS = NP + J;
 	__shared__ double scratch[FIN_THREADS / 32];
+	__shared__ double s_lp;
 	const int gw = blockIdx.x;
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31;
 	if (gw >= A.nwalk) return;
+	// prologue (before the preceding kernel -- the chunk kernel -- has finished): inputs of the accept/reject,
+	// all written by the prep kernel or earlier
+	const bool acc_warp = A.AC.enabled && (tid >> 5) == FIN_THREADS / 32 - 1;
+	AcceptPre pre;
+	if (acc_warp) sampler_accept_prefetch(A.AC.S, A.AC.step, A.AC.half, gw, lane, pre);
+	pdl_wait();
+	pdl_trigger();
 	if (A.skip_if_clean && (*A.nbad == 0 || !A.wbad[gw])) return;  // second invocation: flagged walkers only
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
+	if ((fl & WF_VALID) && (fl & WF_GENERIC)) return;  // written by gp_generic_kernel
 	if (!(fl & WF_VALID)) {
 		if (tid == 0) {
 			if (A.wbad) A.wbad[gw] = 0;
-			if (A.AC.enabled) sampler_accept_one(A.AC.S, A.AC.step, A.AC.half, gw, -CUDART_INF, A.AC.slot);
 			A.lp[gw] = -CUDART_INF;
 			if (A.parts) {
 				A.parts[4 * gw + 0] = pp[PP_LNPRIOR];
@@ -1303,22 +1560,39 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 				A.parts[4 * gw + 3] = CUDART_NAN;
 			}
 		}
+		if (acc_warp) sampler_accept_commit(A.AC.S, pre, gw, -CUDART_INF, A.AC.slot, lane);
 		return;
 	}
-	if (fl & WF_GENERIC) return;  // written by gp_generic_kernel
-	const int J = 2 * A.nterms, NP = J * (J + 1) / 2, CS = NP + J;
 	double q = 0.0, ld = 0.0;
 	for (int k = tid; k < A.nchunks; k += FIN_THREADS) {
 		ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
 		q += pr.quad;
 		ld += pr.logdet;
 	}
+	// carries of this thread's first boundary, requested before the sums synchronise the block
+	const bool do_verify = A.verify && A.nchunks > 1;
+	double ct0[CS], ce0[CS];
+	ChunkPartial pr0;
+	pr0.quad = pr0.logdet = pr0.zmax = 0.0;
+	pr0.dmin = 1.0;
+	const int k0 = 1 + tid;
+	if (do_verify && k0 < A.nchunks) {
+		const double *ct = A.carryT + ((size_t)gw * A.nchunks + k0) * CS;
+		const double *ce = A.carryE + ((size_t)gw * A.nchunks + k0) * CS;
+#pragma unroll
+		for (int i = 0; i < CS; i++) {
+			ct0[i] = ct[i];
+			ce0[i] = ce[i];
+		}
+		pr0 = A.partial[(size_t)gw * A.nchunks + k0];
+	}
 	const double quad = block_sum(q, scratch);
 	const double logdet = block_sum(ld, scratch);
 	int walker_bad = 0;
-	if (A.verify && A.nchunks > 1) {
-		double ua[2 * MAX_TERMS];
-		for (int k = 0; k < A.nterms; k++) {
+	if (do_verify) {
+		double ua[J];
+#pragma unroll
+		for (int k = 0; k < NT; k++) {
 			double a = pp[PP_TERMS + 4 * k], b = pp[PP_TERMS + 4 * k + 1];
 			ua[2 * k] = ua[2 * k + 1] = sqrt(a * a + b * b);
 		}
@@ -1327,29 +1601,38 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 		const double Hh = fmax((double)A.H, 16.0);
 		double worst = 0.0;
 		int nbad = 0;
-		for (int k = 1 + tid; k < A.nchunks; k += FIN_THREADS) {
-			const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
-			const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
-			ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
-			double eS = 0.0, ef = 0.0, nS = 0.0, nf = 0.0;
-			int idx = 0;
-			for (int i = 0; i < J; i++)
-				for (int j = i; j < J; j++, idx++) {
-					const double wgt = (i == j ? 1.0 : 2.0) * ua[i] * ua[j];
-					eS += wgt * fabs(ct[idx] - ce[idx]);
-					nS += wgt * fabs(ct[idx]);
+		for (int k = k0; k < A.nchunks; k += FIN_THREADS) {
+			if (k != k0) {
+				const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
+				const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
+#pragma unroll
+				for (int i = 0; i < CS; i++) {
+					ct0[i] = ct[i];
+					ce0[i] = ce[i];
 				}
+				pr0 = A.partial[(size_t)gw * A.nchunks + k];
+			}
+			double eS = 0.0, ef = 0.0, nS = 0.0, nf = 0.0;
+#pragma unroll
+			for (int i = 0; i < J; i++)
+#pragma unroll
+				for (int j = i; j < J; j++) {
+					const double wgt = (i == j ? 1.0 : 2.0) * ua[i] * ua[j];
+					eS += wgt * fabs(ct0[tri(i, j, J)] - ce0[tri(i, j, J)]);
+					nS += wgt * fabs(ct0[tri(i, j, J)]);
+				}
+#pragma unroll
 			for (int i = 0; i < J; i++) {
-				ef += ua[i] * fabs(ct[NP + i] - ce[NP + i]);
-				nf += ua[i] * fabs(ct[NP + i]);
+				ef += ua[i] * fabs(ct0[NP + i] - ce0[NP + i]);
+				nf += ua[i] * fabs(ct0[NP + i]);
 			}
 			// The halo started from a zero carry, i.e. from an error as large as the state itself, and
 			// left eS (ef) of it after H steps: a geometric decay whose remaining sum over the chunk is
 			// at most H / ln(initial / final) first-step errors (never taken below H / 30).
 			const double GS = Hh / fmin(fmax(log(fmax(nS, 1e-300) / fmax(eS, 1e-300)), 8.0), 30.0);
 			const double Gf = Hh / fmin(fmax(log(fmax(nf, 1e-300) / fmax(ef, 1e-300)), 8.0), 30.0);
-			double errL = eS / pr.dmin * GS;
-			double errQ = 2.0 * ef * pr.zmax * Gf;
+			double errL = eS / pr0.dmin * GS;
+			double errQ = 2.0 * ef * pr0.zmax * Gf;
 			double r = fmax(errL / budL, errQ / budQ);
 			bool bad = !(r <= 1.0);  // NaN -> redo
 			if (isfinite(r)) worst = fmax(worst, r);
@@ -1362,7 +1645,7 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
 			worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
 		}
-		if ((tid & 31) == 0) {
+		if (lane == 0 && (nbad || worst > 0.0)) {
 			if (nbad) {
 				atomicAdd(A.nbad, nbad);
 				atomicAdd(A.acc, (unsigned long long)nbad);
@@ -1382,15 +1665,19 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			lnl = -CUDART_INF;
 		}
 		A.lp[gw] = lp;
+		s_lp = lp;
 		if (A.parts) {
 			A.parts[4 * gw + 0] = lnprior;
 			A.parts[4 * gw + 1] = quad;
 			A.parts[4 * gw + 2] = logdet;
 			A.parts[4 * gw + 3] = lnl;
 		}
+	}
+	if (A.AC.enabled) {
 		// a walker without a flagged chunk is final now; a flagged one is decided by the second
 		// invocation, after pass 2 has repaired its chunks
-		if (A.AC.enabled && !walker_bad) sampler_accept_one(A.AC.S, A.AC.step, A.AC.half, gw, lp, A.AC.slot);
+		__syncthreads();
+		if (acc_warp && !walker_bad) sampler_accept_commit(A.AC.S, pre, gw, s_lp, A.AC.slot, lane);
 	}
 }
 
@@ -1407,6 +1694,8 @@ struct GenericArgs {
 
 __global__ void gp_generic_kernel(GenericArgs A)
 {
+	pdl_wait();
+	pdl_trigger();
 	const int gw = blockIdx.x * blockDim.x + threadIdx.x;
 	if (gw >= A.nwalk) return;
 	const int fl = A.flags[gw];
@@ -1506,6 +1795,8 @@ struct DiagArgs {
 
 __global__ void diag_kernel(DiagArgs A)
 {
+	pdl_wait();
+	pdl_trigger();
 	const int lane = threadIdx.x & 31;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= A.nwalk) return;
@@ -1728,6 +2019,8 @@ __global__ void predict_points_kernel(PredictArgs A, const double *xs_days, long
 // one block per star: random half/half split (emcee RedBlueMove with randomize_split=True)
 __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 {
+	pdl_wait();
+	pdl_trigger();
 	extern __shared__ unsigned long long s_keys[];
 	int *s_set = (int *)(s_keys + S.W);
 	const int star = blockIdx.x;
@@ -1760,6 +2053,8 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 // standalone accept/reject (models whose log-probability is not produced by gp_finalize_kernel)
 __global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int half, long long slot)
 {
+	pdl_wait();
+	pdl_trigger();
 	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
 	if (gi >= S.nstars * (S.W / 2)) return;
 	sampler_accept_one(S, step, half, gi, S.lq[gi], slot);

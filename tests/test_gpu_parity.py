@@ -578,3 +578,71 @@ def test_eccentric_and_odd_transit_parameters_through_the_posterior(engine):
         assert_parts_close(parts, want)
     engine.set_option("chunks", 0)
     assert np.isfinite(want_lp).sum() >= 30
+
+
+def test_sampler_speculative_block_is_replayed_with_repair(engine):
+    """The sampler runs blocks of steps without the repair pass and replays a block when the chunk
+    verification flagged anything.  With a useless halo every block is replayed; the chain must still be
+    the oracle's, and equal to a run with the speculation switched off."""
+    t, y, yerr = synthetic_star(6000, 4)
+    np.random.seed(8)
+    gp = GPModel(C3_CONFIG_GP)
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    W, nsteps = 32, 7
+    init = np.hstack([gp.sample_prior(W), tr.sample_prior(W)])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    ochain, ologp, onacc = oracle.sample(spec, t, y, yerr, init, nsteps, seed=77)
+    engine.set_option("chunks", 12)
+    engine.set_option("halo", 2)
+    engine.set_option("adapt_every", 3)          # blocks of 3, 3 and 1 steps
+    try:
+        before = engine.stat("spec_replays")
+        chain, logp, nacc = engine.sample(init, nsteps, seed=77)
+        assert engine.stat("spec_replays") >= before + 3
+        assert np.array_equal(nacc, onacc)
+        assert rel(chain, ochain) < 1e-9
+        fin = np.isfinite(ologp)
+        assert rel(logp[fin], ologp[fin]) < 1e-9
+        engine.set_option("speculate", 0)
+        chain2, logp2, nacc2 = engine.sample(init, nsteps, seed=77)
+        assert np.array_equal(chain2, chain) and np.array_equal(logp2, logp) and np.array_equal(nacc2, nacc)
+    finally:
+        engine.set_option("speculate", 1)
+        engine.set_option("adapt_every", 32)
+        engine.set_option("chunks", 0)
+        engine.set_option("halo", 0)
+
+
+@pytest.mark.parametrize("jitter", [0.0, 3e-11, 5e-9, 5e-7, 1e-5])
+def test_regular_step_treatments_agree(engine, jitter):
+    """The fast loop advances the generators by the tile's constant cadence when the accumulated timing
+    deviation is negligible (order 0) and by a series of order 1..3 in the per-step deviation otherwise;
+    option series_order_min forces the higher treatments, 4 being the general loop with exp / sincos.
+    All of them must give the oracle's numbers on an exact grid and on grids with timing jitter."""
+    t, y, yerr = synthetic_star(9000, 21)
+    if jitter:
+        t = t + np.random.default_rng(2).uniform(-jitter, jitter, t.size)
+    np.random.seed(5)
+    gp = GPModel(C3_CONFIG_GP)
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    theta = np.hstack([gp.sample_prior(32), tr.sample_prior(32)])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    try:
+        for order in (0, 1, 2, 3, 4):
+            engine.set_option("series_order_min", order)
+            for chunks in (1, 6):
+                engine.set_option("chunks", chunks)
+                lp, parts = engine.log_prob(theta, return_parts=True)
+                assert_parts_close(parts, want)
+    finally:
+        engine.set_option("series_order_min", 0)
+        engine.set_option("chunks", 0)
