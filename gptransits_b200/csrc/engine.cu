@@ -836,6 +836,8 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	// is negligible the loop advances by the tile's constant cadence and ignores the per-step deviation.
 	double dreg = 1e-3 * std::fabs(dt0), dmax = 0.0, cdev = 0.0;
 	for (int64_t tl = 0; tl < ntiles; tl++) tile_dt0[tl] = dt0;
+	double prev_base = 0.0;
+	bool have_prev = false;
 	for (int64_t tl = 0; tl < ntiles; tl++) {
 		const int64_t n_lo = tl * TILE, n_hi = std::min<int64_t>(N, n_lo + TILE);
 		double sum = 0.0;
@@ -845,19 +847,41 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 				sum += h[n].x - dt0;
 				cnt++;
 			}
-		if (cnt) tile_dt0[tl] = dt0 + sum / (double)cnt;
-		double run = 0.0, lo = 0.0, hi = 0.0;
-		for (int64_t n = n_lo; n < n_hi; n++) {
-			if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) {
-				dmax = std::max(dmax, std::fabs(h[n].x - tile_dt0[tl]));
-				run += h[n].x - tile_dt0[tl];
-				lo = std::min(lo, run);
-				hi = std::max(hi, run);
-				cdev = std::max(cdev, hi - lo);
-			} else {
-				run = lo = hi = 0.0;
+		// largest accumulated deviation and largest single deviation of the tile for a base cadence
+		auto tile_dev = [&](double base, double &dsingle) {
+			double run = 0.0, lo = 0.0, hi = 0.0, worst = 0.0;
+			dsingle = 0.0;
+			for (int64_t n = n_lo; n < n_hi; n++) {
+				if (n > 0 && std::fabs(h[n].x - dt0) <= dreg) {
+					dsingle = std::max(dsingle, std::fabs(h[n].x - base));
+					run += h[n].x - base;
+					lo = std::min(lo, run);
+					hi = std::max(hi, run);
+					worst = std::max(worst, hi - lo);
+				} else {
+					run = lo = hi = 0.0;
+				}
+			}
+			return worst;
+		};
+		double base = cnt ? dt0 + sum / (double)cnt : dt0;
+		double ds = 0.0, dev = tile_dev(base, ds);
+		// keep the previous tile's base when it serves this tile about as well (on an exact grid the tile
+		// means differ by rounding only): the kernels recompute their per-walker constants only on a change
+		if (have_prev && prev_base != base) {
+			double ds_p = 0.0;
+			const double dev_p = tile_dev(prev_base, ds_p);
+			if (dev_p <= 1.5 * dev) {
+				base = prev_base;
+				dev = dev_p;
+				ds = ds_p;
 			}
 		}
+		tile_dt0[tl] = base;
+		prev_base = base;
+		have_prev = true;
+		dmax = std::max(dmax, ds);
+		cdev = std::max(cdev, dev);
 	}
 	s.N = (int)N;
 	s.dt0 = dt0;
@@ -1059,13 +1083,20 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		return GPT_OK;
 	};
 	auto run_steps = [&](int64_t sa, int64_t sb, bool speculative) -> int {
+		CK(e->s_act.ensure((size_t)(sb - sa) * ns * W));
 		for (int64_t s = sa; s < sb; s++) {
 			if (ms_per_step) {
 				if (flush_l2) CK(cudaMemsetAsync(flush.p, (int)(s & 0xff), flush_bytes, st));
 				CK(cudaEventRecord(ev[2 * s], st));
 			}
-			launch_k(sampler_split_kernel, dim3(ns), dim3(256), (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st, S, e->s_step);
-			e->n_launch++;
+			if (s == sa) {
+				// the random splits of all steps of the block: one launch (they depend on the RNG stream
+				// only); inside the first step's timed region
+				S.act = e->s_act.p;
+				launch_k(sampler_split_kernel, dim3(ns, (unsigned)(sb - sa)), dim3(256), (size_t)W * (sizeof(unsigned long long) + sizeof(int)), st, S, e->s_step);
+				e->n_launch++;
+			}
+			S.act = e->s_act.p + (size_t)(s - sa) * ns * W;
 			for (int half = 0; half < 2; half++) {
 				PrepPropose pr;
 				pr.enabled = 1;
@@ -1110,7 +1141,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	// to the start of the block and the block is replayed with the repair pass -- the RNG is counter
 	// based, so the replay reproduces the same moves and the result does not depend on the speculation.
 	const bool can_speculate = e->opt_speculate && !e->may_generic && e->opt_verify;
-	const int64_t block = e->opt_adapt_every > 0 ? e->opt_adapt_every : 64;
+	const int64_t block = e->opt_adapt_every > 0 ? std::min(e->opt_adapt_every, 1024) : 64;
 	const size_t nw = (size_t)ns * W;
 	for (int64_t sa = 0; sa < nsteps; sa += block) {
 		const int64_t sb = std::min<int64_t>(nsteps, sa + block);

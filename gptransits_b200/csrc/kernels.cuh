@@ -571,6 +571,7 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 // exactly the samples for which the GP kernels will read mean[].  Walkers whose window covers
 // everything are swept by the whole CTA.
 constexpr int EPOCH_SCAN_CAP = 6144;  // items gathered per flush (24 KB of shared memory)
+constexpr int SCAN_COARSE = 2048;     // entries of the coarse time table (16 KB of shared memory)
 
 __global__ void __launch_bounds__(TR_THREADS)
 transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
@@ -611,9 +612,43 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 	// The walker's items are gathered in shared memory and appended to the global queue with ONE
 	// atomic per flush (a single global counter cannot take tens of thousands of atomics per launch).
 	__shared__ unsigned int s_items[EPOCH_SCAN_CAP];
+	__shared__ double s_coarse[SCAN_COARSE];  // every cstride-th sample time: the search starts in shared memory
 	__shared__ unsigned int s_n, s_base;
+	int cstride = TILE;
+	while ((N + cstride - 1) / cstride > SCAN_COARSE) cstride <<= 1;
+	const int ncoarse = (N + cstride - 1) / cstride;
+	for (int i = threadIdx.x; i < ncoarse; i += blockDim.x) s_coarse[i] = t[(size_t)i * cstride];
 	if (threadIdx.x == 0) s_n = 0;
 	__syncthreads();
+	const double dt_med = st.dt0 / kDaysToMs;
+	// first sample with t >= lo: bisection over the coarse table (shared memory), an interpolated guess
+	// inside the stride checked with two loads issued together, bisection of whatever bracket remains
+	auto lower_bound = [&](double lo) -> int {
+		int ca = 0, cb = ncoarse;
+		while (ca < cb) {
+			const int md = (ca + cb) >> 1;
+			if (s_coarse[md] < lo) ca = md + 1; else cb = md;
+		}
+		if (ca == 0) return 0;
+		int a = (ca - 1) * cstride + 1, b = min(N, ca * cstride);
+		const double tl0 = s_coarse[ca - 1];
+		const double dtl = ca < ncoarse ? (s_coarse[ca] - tl0) / cstride : dt_med;
+		const double gf = ceil((lo - tl0) / dtl);
+		int g = (ca - 1) * cstride + (gf < (double)cstride ? (int)gf : cstride);
+		g = min(max(g, a), b);
+		const double tg = t[min(g, N - 1)], tgm = t[g - 1];
+		if (g < b) {
+			if (tg < lo) a = g + 1; else b = g;
+		}
+		if (g - 1 >= a && g - 1 < b) {
+			if (tgm < lo) a = max(a, g); else b = g - 1;
+		}
+		while (a < b) {
+			const int md = (a + b) >> 1;
+			if (t[md] < lo) a = md + 1; else b = md;
+		}
+		return a;
+	};
 	const long long nk = kmax - kmin + 1;
 	const long long rounds = (nk + blockDim.x - 1) / blockDim.x;
 	bool overflow = false;
@@ -621,6 +656,8 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 		const long long k = kmin + rd * blockDim.x + threadIdx.x;
 		int a = 0, cnt = 0;
 		double hi = 0.0;
+		unsigned long long mask = 0ull;  // in-window flags of samples a .. a+63
+		bool longer = false;             // the epoch's range goes on past a+63
 		if (k <= kmax) {
 			const double tc = wcen + (double)k * pa;
 			const double half = whalf * pa;
@@ -628,20 +665,39 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 			const double lo = tc - half - eps;
 			hi = tc + half + eps;
 			if (!(hi < t[0] || lo > t[N - 1])) {
-				int b = N;  // first sample with t >= lo
-				while (a < b) {
-					const int mid = (a + b) >> 1;
-					if (t[mid] < lo) a = mid + 1; else b = mid;
+				a = lower_bound(lo);
+				bool more = true;
+#pragma unroll 1
+				for (int blk = 0; blk < 4 && more; blk++) {
+					double tv[16];
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						const int n = a + 16 * blk + j;
+						tv[j] = n < N ? t[n] : CUDART_INF;
+					}
+#pragma unroll
+					for (int j = 0; j < 16; j++)
+						if (tv[j] <= hi && in_transit_window(tv[j], wcen, inv_per, whalf)) mask |= 1ull << (16 * blk + j);
+					more = tv[15] <= hi;
 				}
-				for (int n = a; n < N && t[n] <= hi; n++) cnt += in_transit_window(t[n], wcen, inv_per, whalf) ? 1 : 0;
+				longer = more;
+				cnt = __popcll(mask);
+				if (longer)
+					for (int n = a + 64; n < N && t[n] <= hi; n++) cnt += in_transit_window(t[n], wcen, inv_per, whalf) ? 1 : 0;
 			}
 		}
 		const unsigned int pos = cnt ? atomicAdd(&s_n, (unsigned int)cnt) : 0u;
 		const bool fits = pos + (unsigned int)cnt <= (unsigned int)EPOCH_SCAN_CAP;
 		if (cnt && fits) {
 			unsigned int q = pos;
-			for (int n = a; n < N && t[n] <= hi; n++)
-				if (in_transit_window(t[n], wcen, inv_per, whalf)) s_items[q++] = (unsigned int)n;
+			while (mask) {
+				const int j = __ffsll((long long)mask) - 1;
+				mask &= mask - 1;
+				s_items[q++] = (unsigned int)(a + j);
+			}
+			if (longer)
+				for (int n = a + 64; n < N && t[n] <= hi; n++)
+					if (in_transit_window(t[n], wcen, inv_per, whalf)) s_items[q++] = (unsigned int)n;
 		}
 		if (__syncthreads_or(cnt && !fits)) {
 			overflow = true;
@@ -1061,6 +1117,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 
 	__shared__ __align__(128) double4 s_tile[NSTAGE][TILE];
 	__shared__ __align__(8) uint64_t s_bar[NSTAGE];
+	__shared__ double s_ab[2 * NT][CHUNK_THREADS];  // celerite (a, b) of each thread's walker: needed at anchors only
 
 	const int c = blockIdx.x;
 	const int w = blockIdx.y * blockDim.x + threadIdx.x;  // blockDim.x = min(128, walkers rounded to a warp)
@@ -1099,7 +1156,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	double xdev = 0.0;                              // max |c|, |d| times the accumulated deviation of a run
 	double cdt = 0.0;                               // max c dt0: decay of the scale over one step
 #pragma unroll
-	for (int k = 0; k < NT; k++) K.c[k] = K.d[k] = 0.0;
+	for (int k = 0; k < NT; k++) {
+		K.c[k] = K.d[k] = 0.0;
+		s_ab[2 * k][threadIdx.x] = s_ab[2 * k + 1][threadIdx.x] = 0.0;
+	}
 	if (active) {
 		asum = pp[PP_ASUM];
 #pragma unroll
@@ -1107,6 +1167,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 			K.c[k] = pp[PP_TERMS + 4 * k + 2];
 			K.d[k] = pp[PP_TERMS + 4 * k + 3];
 			cdt = fmax(cdt, fabs(K.c[k]));
+			s_ab[2 * k][threadIdx.x] = pp[PP_TERMS + 4 * k + 0];
+			s_ab[2 * k + 1][threadIdx.x] = pp[PP_TERMS + 4 * k + 1];
 		}
 		cdt *= 1.002 * fabs(st.dt0);
 		if (TRANSIT) {
@@ -1193,10 +1255,11 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		prefetch_l1(meanw + hs);
 		prefetch_l1(meanw + min(hs + 16, N - 1));
 	}
-
 	// residual of sample m: flux minus this walker's transit model.  The model array is valid only
-	// inside the walker's window, so it is loaded unconditionally (L1-prefetched, and one full step
-	// ahead of its use in the fast loop) and selected.
+	// inside the walker's window, so it is loaded unconditionally (L1-prefetched line by line, and ahead
+	// of its use in the fast loop) and selected.  (A load predicated on the window test was measured
+	// slower: the divergent branch and the extra shared-memory read cost more than the loads save.)
+	const double4 *tile = nullptr;
 	auto load_mean = [&](int m) -> double {
 		double mv = 0.0;
 		if (TRANSIT && meanw) {
@@ -1219,17 +1282,20 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	};
 
 	double dt0_cur = st.dt0;
+	double dt0_next = st.tile_dt0[t_first];
+	int irr_next = ip < st.nirr ? st.irr[ip] : INT_MAX;  // next irregular sample at or after the cursor
 	for (int tl = t_first; tl <= t_last; tl++) {
 		const int it = tl - t_first;
 		const int stg = it % NSTAGE;
 		mbar_wait(&s_bar[stg], (uint32_t)((it / NSTAGE) & 1));
 		const int s0 = max(tl * TILE, hs), s1 = min((tl + 1) * TILE, n1);
-		const double4 *tile = &s_tile[stg][0] - tl * TILE;
+		tile = &s_tile[stg][0] - tl * TILE;
 		const bool store_here = (!pass2 && c > 0 && active && n0 >= s0 && n0 < s1);
 		double *const cdst = A.carryE + ((size_t)gw * A.nchunks + c) * CS;
 
-		// per-tile base cadence (recomputed only when it changes)
-		const double dt0t = st.tile_dt0[tl];
+		// per-tile base cadence (recomputed only when it changes; the next tile's is requested now)
+		const double dt0t = dt0_next;
+		dt0_next = st.tile_dt0[min(tl + 1, t_last)];
 		if (dt0t != dt0_cur) {
 			dt0_cur = dt0t;
 			if (order < 4) K.set_base(dt0t);
@@ -1244,11 +1310,11 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 				phiC[k] = exp(-K.c[k] * sm.x);
 				double sn_, cs_;
 				sincos(K.d[k] * x, &sn_, &cs_);
-				const double a = pp[PP_TERMS + 4 * k + 0], b = pp[PP_TERMS + 4 * k + 1];
+				const double a = s_ab[2 * k][threadIdx.x], b = s_ab[2 * k + 1][threadIdx.x];  // 0 for inactive threads
 				VC[2 * k] = cs_;
 				VC[2 * k + 1] = sn_;
-				UC[2 * k] = active ? fma(a, cs_, b * sn_) : 0.0;
-				UC[2 * k + 1] = active ? fma(a, sn_, -(b * cs_)) : 0.0;
+				UC[2 * k] = fma(a, cs_, b * sn_);
+				UC[2 * k + 1] = fma(a, sn_, -(b * cs_));
 			}
 			yC = residual(sm, r);
 			AC = sm.z + asum;
@@ -1337,9 +1403,11 @@ GP_PRAGMA_UNROLL
 			};
 			int a_ = s0;
 			while (a_ < s1) {
-				while (ip < st.nirr && st.irr[ip] <= a_) ip++;  // next irregular sample after a_
-				int r = ip < st.nirr ? min(st.irr[ip], s1) : s1;
-				r = min(r, a_ + runlen);
+				while (irr_next <= a_) {  // next irregular sample after a_
+					ip++;
+					irr_next = ip < st.nirr ? st.irr[ip] : INT_MAX;
+				}
+				int r = min(min(irr_next, s1), a_ + runlen);
 				const bool store_now = store_here && a_ <= n0 && n0 < r;
 				if (store_now && n0 == a_) store_carry(cdst);
 				first_step(a_, a_ >= n0);
@@ -2016,8 +2084,10 @@ __global__ void predict_points_kernel(PredictArgs A, const double *xs_days, long
 }
 
 // ================================================================== sampler
-// one block per star: random half/half split (emcee RedBlueMove with randomize_split=True)
-__global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
+// one block per (star, step): random half/half split (emcee RedBlueMove with randomize_split=True).  The
+// split depends on the RNG stream only, so one launch prepares the index lists of a whole block of steps:
+// step0 + blockIdx.y writes its lists at S.act + blockIdx.y * nstars * W.
+__global__ void sampler_split_kernel(SamplerDev S, unsigned long long step0)
 {
 	pdl_wait();
 	pdl_trigger();
@@ -2025,6 +2095,8 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step)
 	int *s_set = (int *)(s_keys + S.W);
 	const int star = blockIdx.x;
 	const int W = S.W, H = W / 2;
+	const unsigned long long step = step0 + blockIdx.y;
+	S.act += (size_t)blockIdx.y * S.nstars * W;
 	const uint32_t sid = (uint32_t)S.star_ids[star];
 	for (int w = threadIdx.x; w < W; w += blockDim.x) {
 		uint32_t r[4];
