@@ -317,7 +317,7 @@ def run_ours(args):
     eng.set_option("reset_timers", 1)
     eng.set_option("time_kernels", 1)
     ms2 = eng.sampler_run_timed(args.steps, keep=True, flush_l2=flush)
-    kern = {k: (eng.stat("ms_" + k), eng.stat("n_" + k)) for k in ("prep", "transit", "chunk", "final", "pass2")}
+    kern = {k: (eng.stat("ms_" + k), eng.stat("n_" + k)) for k in ("prep", "transit", "trscan", "chunk", "final", "pass2")}
     eng.set_option("time_kernels", 0)
     clk = clocks.stop()
     _, _, nacc = eng.sampler_state()
@@ -423,6 +423,7 @@ def run_ours(args):
                          "hbm_algorithmic_bytes_per_launch": bytes_per_launch, "traffic": traffic,
                          "hbm_view": hbm_view(bytes_per_launch, chunk_ms / max(chunk_n, 1)),
                          "kernel_share_of_step": {k: v[0] / float(ms2.sum()) for k, v in kern.items()},
+                         "kernel_us_per_launch": {k: 1e3 * v[0] / max(v[1], 1) for k, v in kern.items()},
                          "pass2_chunks": stats["pass2_chunks"], "verify_ratio": stats["verify_ratio"]},
             "clocks": clk,
         }

@@ -85,7 +85,8 @@ struct gpt_engine {
 	int opt_adapt_every = 32;  // sampler steps between halo adaptations
 	int opt_transit_strict = 0;
 	int opt_series_order_min = 0;
-	int opt_speculate = 1;
+	int opt_speculate = 0;   // speculative sampler blocks (no repair launches, replay on a flagged chunk): see sampler_run_impl
+	int spec_clean = 2;  // consecutive clean blocks; a block runs speculatively after two (a flagged one resets it)
 	long long n_spec_replays = 0;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
@@ -180,9 +181,19 @@ struct gpt_engine {
 		double lr0 = std::log(1e12), lr = std::log(r), lt = std::log(0.3);
 		double want = H * (lr0 - lt) / std::max(lr0 - lr, 1.0);
 		int nh = (int)std::ceil(want / 16.0) * 16;
-		nh = std::max(32, std::min(nh, 4096));
+		nh = std::max(32, std::min(nh, 32768));
+		// hysteresis: a halo at which a chunk was flagged is not tried again for a while (the model above
+		// would otherwise shrink back to it and fail again, and a flagged block costs a repair or a replay)
+		if (failed) {
+			fail_halo = std::max(fail_halo, H);
+			fail_age = 0;
+		} else if (++fail_age > 64) {
+			fail_halo = 0;
+		}
+		if (fail_halo > 0) nh = std::max(nh, fail_halo + 16);
 		cur_halo = nh > cur_halo ? nh : std::max(nh, (int)(cur_halo * 0.75));
 	}
+	int fail_halo = 0, fail_age = 0;
 
 	void set_error(const std::string &m) { err = m; }
 };
@@ -260,7 +271,7 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 	} else {
 		// Cost model (measured on B200): every thread runs N/nc + H dependent steps; up to one warp
 		// per SM sub-partition they all run concurrently at the single-warp step time, two resident
-		// warps share the FP64 pipe at 1.32x the single-warp throughput, more warps queue up.
+		// warps share the FP64 pipe at 1.21x the single-warp throughput, more warps queue up.
 		const int cthreads = std::min(CHUNK_THREADS, ((W + 31) / 32) * 32);
 		const double wpl = (double)nstars * ((W + cthreads - 1) / cthreads) * (cthreads / 32);  // warps per chunk layer
 		const double slots = 148.0 * 4.0;
@@ -271,7 +282,7 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 			const double h = cand == 1 ? 0.0 : (double)H;
 			const double wps = cand * wpl / slots;
 			double slow = 1.0;
-			if (wps > 1.0) slow = wps <= 2.0 ? 1.0 + (wps - 1.0) * (2.0 / 1.32 - 1.0) : wps / 1.32;
+			if (wps > 1.0) slow = wps <= 2.0 ? 1.0 + (wps - 1.0) * (2.0 / 1.21 - 1.0) : wps / 1.21;
 			const double cost = ((double)N / cand + h) * slow + 0.05 * cand;
 			if (cost < best * 0.999) {
 				best = cost;
@@ -778,6 +789,8 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *d)
 		}
 		e->prior_cmin = cmin;
 		e->cur_halo = 0;
+		e->fail_halo = 0;
+		e->fail_age = 0;
 	}
 	e->model = m;
 	e->may_generic = may_generic;
@@ -1030,6 +1043,7 @@ int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	e->sampling = true;
+	e->spec_clean = 2;
 	return GPT_OK;
 }
 
@@ -1066,7 +1080,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
 	// verification verdicts accumulate on the device; every "adapt_every" steps (and at the end) they
 	// are read back -- one small synchronisation -- to steer the halo length
-	auto adapt = [&](bool *flagged) -> int {
+	auto adapt = [&](bool *flagged, bool speculative) -> int {
 		unsigned long long acc[2] = {0, 0};
 		CK(cudaMemcpyAsync(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
@@ -1075,7 +1089,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		memcpy(&ratio, &acc[1], sizeof(double));
 		e->last_verr = ratio;
 		if (flagged) *flagged = acc[0] > 0;
-		if (acc[0] && !flagged) {
+		if (acc[0] && !speculative) {
 			e->n_pass2_calls++;
 			e->n_pass2_chunks += (long long)acc[0];
 		}
@@ -1135,7 +1149,10 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	};
 	if (ms_per_step)
 		for (int64_t s = 0; s < nsteps; s++) ms_per_step[s] = 0.f;
-	// Blocks of "adapt_every" steps.  A block runs speculatively: no repair pass is enqueued, the chunk
+	// Blocks of "adapt_every" steps.  With option "speculate" (off by default: the two idle repair launches
+	// per half-step cost only ~1 % of a C3 step, a replay costs a whole block, and light curves whose chunks
+	// are flagged now and then -- the bundled examples -- lose more than they gain) a block runs
+	// speculatively: no repair pass is enqueued, the chunk
 	// verification only accumulates its verdicts on the device.  They are read once per block (one small
 	// synchronisation, also used to steer the halo); if any chunk was flagged the ensemble is rolled back
 	// to the start of the block and the block is replayed with the repair pass -- the RNG is counter
@@ -1147,7 +1164,8 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		const int64_t sb = std::min<int64_t>(nsteps, sa + block);
 		const unsigned long long step_at = e->s_step;
 		const long long kept_at = e->s_kept;
-		if (can_speculate) {
+		const bool spec = can_speculate && e->spec_clean >= 2;
+		if (spec) {
 			CK(e->s_snap_x.ensure(nw * ndim));
 			CK(e->s_snap_lpx.ensure(nw));
 			CK(e->s_snap_nacc.ensure(nw));
@@ -1155,14 +1173,17 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 			CK(cudaMemcpyAsync(e->s_snap_lpx.p, S.lpx, nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
 			CK(cudaMemcpyAsync(e->s_snap_nacc.p, S.nacc, nw * sizeof(long long), cudaMemcpyDeviceToDevice, st));
 		}
-		int rc = run_steps(sa, sb, can_speculate);
+		int rc = run_steps(sa, sb, spec);
 		if (rc) return rc;
 		bool flagged = false;
-		rc = adapt(can_speculate ? &flagged : nullptr);
+		rc = adapt(&flagged, spec);
 		if (rc) return rc;
 		rc = add_times(sa, sb);
 		if (rc) return rc;
-		if (can_speculate && flagged) {
+		// speculation pays only while flagged chunks are rare: after a block with one, blocks run with the
+		// repair pass enqueued (no replay possible) until two in a row come back clean
+		e->spec_clean = flagged ? 0 : std::min(e->spec_clean + 1, 2);
+		if (spec && flagged) {
 			e->n_spec_replays++;
 			CK(cudaMemcpyAsync(S.x, e->s_snap_x.p, nw * ndim * sizeof(double), cudaMemcpyDeviceToDevice, st));
 			CK(cudaMemcpyAsync(S.lpx, e->s_snap_lpx.p, nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1171,7 +1192,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 			e->s_kept = kept_at;
 			rc = run_steps(sa, sb, false);
 			if (rc) return rc;
-			rc = adapt(nullptr);
+			rc = adapt(nullptr, false);
 			if (rc) return rc;
 			rc = add_times(sa, sb);
 			if (rc) return rc;
