@@ -106,6 +106,9 @@ struct gpt_engine {
 	DevBuf<unsigned char> d_redo;
 	DevBuf<unsigned long long> d_queue;  // transit work queue: (walker << 32) | sample
 	DevBuf<unsigned int> d_qcount;
+	DevBuf<unsigned int> d_qfused;  // [0] item counter of the fused prep + scan path (zero between evaluations), [1] last count
+	bool last_fused = false;
+	int opt_fuse_scan = 1;
 	DevBuf<int> d_nbad;      // [1]
 	DevBuf<double> d_verr;   // [1]
 	char *h_stage = nullptr;  // pinned staging buffer of gpt_star_upload (grow-only)
@@ -411,15 +414,28 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		CK(e->d_qcount.ensure(1));
 	}
 
+	// small batches: the epoch scan rides on the prep kernel (one launch, the window never leaves the CTA)
+	const bool fuse_scan = m.has_transit && nwalk <= 4096 && e->opt_epoch_scan && e->opt_fuse_scan;
+	if (fuse_scan && !e->d_qfused.p) {
+		CK(e->d_qfused.ensure(2));
+		CK(cudaMemsetAsync(e->d_qfused.p, 0, 2 * sizeof(unsigned int), st));
+	}
+	e->last_fused = fuse_scan;
+	unsigned int *qcount = fuse_scan ? e->d_qfused.p : e->d_qcount.p;
 	e->timer_begin(TK_PREP);
 	PrepReset reset;
 	reset.wstatus = e->d_wstatus.p; reset.nbad = e->d_nbad.p; reset.verr = e->d_verr.p;
-	reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
+	reset.qcount = (m.has_transit && !fuse_scan) ? e->d_qcount.p : nullptr;
 	PrepPropose pr;
 	memset(&pr, 0, sizeof(pr));
 	if (propose) pr = *propose;
+	PrepScan sc;
+	sc.enabled = fuse_scan ? 1 : 0;
+	sc.queue = e->d_queue.p;
+	sc.qcount = qcount;
 	if (nwalk <= 4096)
-		launch_k(prep_kernel, dim3(nwalk), dim3(PREP_THREADS), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
+		launch_k(prep_kernel, dim3(nwalk), dim3(fuse_scan ? PREP_SCAN_THREADS : PREP_THREADS), 0, st, m, dst, W, d_theta, nwalk,
+			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	else
 		launch_k(prep_wide_kernel, dim3((nwalk + 63) / 64), dim3(64), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
 	e->timer_end(TK_PREP);
@@ -427,22 +443,24 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	if (m.has_transit) {
 		dim3 g(nwalk, (N + TR_THREADS - 1) / TR_THREADS);
 		e->timer_begin(TK_TRANSIT);
-		e->timer_begin(TK_TRSCAN);
-		if (e->opt_epoch_scan)
-		{
-			// one thread per transit epoch: a few per 256 samples at most for any realistic period
-			int et = 32;
-			while (et < TR_THREADS && et * 256 < N) et *= 2;
-			launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p);
+		if (!fuse_scan) {
+			e->timer_begin(TK_TRSCAN);
+			if (e->opt_epoch_scan) {
+				// one thread per transit epoch: a few per 256 samples at most for any realistic period
+				int et = 32;
+				while (et < TR_THREADS && et * 256 < N) et *= 2;
+				launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, qcount);
+			} else {
+				launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, qcount,
+					 e->d_mean.p, 0);
+			}
+			e->timer_end(TK_TRSCAN);
+			e->n_launch++;
 		}
-		else
-			launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
-								      e->d_mean.p, 0);
-		e->timer_end(TK_TRSCAN);
-		launch_transit_eval(e, st, dst, W, m.supersample, m.exp_time, m.ellip_mode,
-								    e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
+		launch_transit_eval(e, st, dst, W, m.supersample, m.exp_time, m.ellip_mode, e->d_prep.p, e->d_queue.p, qcount,
+				    e->d_mean.p, 0);
 		e->timer_end(TK_TRANSIT);
-		e->n_launch += 2;
+		e->n_launch++;
 	}
 	e->n_evals += nwalk;
 
@@ -451,6 +469,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
 		a.lp = d_lp; a.parts = d_parts; a.W = W; a.nwalk = nwalk; a.N = N;
 		a.gp = m.ncomp > 0; a.transit = m.has_transit; a.has_err = e->stars[star0].has_err;
+		a.qreset = fuse_scan ? e->d_qfused.p : nullptr;
 		launch_k(diag_kernel, dim3((nwalk * 32 + 255) / 256), dim3(256), 0, st, a);
 		e->n_launch++;
 		CK(cudaGetLastError());
@@ -492,6 +511,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	f.acc = e->d_acc.p;
 	f.wbad = e->d_wbad.p;
 	f.tol = e->opt_tol;
+	f.qreset = fuse_scan ? e->d_qfused.p : nullptr;
 	memset(&f.AC, 0, sizeof(f.AC));
 	// the accept/reject can ride on the finalize kernel when every walker's result comes from it
 	if (accept && !e->may_generic && !host_sync) {
@@ -596,7 +616,7 @@ void gpt_engine_destroy(gpt_engine *e)
 	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
 	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
 	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
-	e->d_queue.release(); e->d_qcount.release(); e->d_wbad.release();
+	e->d_queue.release(); e->d_qcount.release(); e->d_qfused.release(); e->d_wbad.release();
 	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
 	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
 	e->s_snap_x.release(); e->s_snap_lpx.release(); e->s_snap_nacc.release();
@@ -627,6 +647,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_transit_strict = value != 0;
 	} else if (k == "series_order_min") {
 		e->opt_series_order_min = std::min(4, std::max(0, (int)value));
+	} else if (k == "fuse_scan") {
+		e->opt_fuse_scan = value != 0;
 	} else if (k == "speculate") {
 		e->opt_speculate = value != 0;
 	} else if (k == "pdl") {
@@ -674,9 +696,10 @@ int gpt_get_stat(gpt_engine *e, const char *key, double *value)
 	else if (k == "nstars") *value = (double)e->stars.size();
 	else if (k == "transit_items") {
 		unsigned int q = 0;
-		if (e->d_qcount.p) {
+		const unsigned int *src = e->last_fused ? (e->d_qfused.p ? e->d_qfused.p + 1 : nullptr) : e->d_qcount.p;
+		if (src) {
 			cudaStreamSynchronize(e->stream);
-			cudaMemcpy(&q, e->d_qcount.p, sizeof(q), cudaMemcpyDeviceToHost);
+			cudaMemcpy(&q, src, sizeof(q), cudaMemcpyDeviceToHost);
 		}
 		*value = q;
 	}
@@ -1391,7 +1414,9 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 		reset.qcount = m.has_transit ? e->d_qcount.p : nullptr;
 		PrepPropose pr;
 		memset(&pr, 0, sizeof(pr));
-		launch_k(prep_kernel, dim3(1), dim3(PREP_THREADS), 0, st, m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr);
+		PrepScan sc;
+		memset(&sc, 0, sizeof(sc));
+		launch_k(prep_kernel, dim3(1), dim3(PREP_THREADS), 0, st, m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	}
 	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);

@@ -212,10 +212,21 @@ struct FinalAccept {
 // Sums are gathered in component / parameter order by one lane, so the arithmetic order does not
 // depend on the launch shape.
 constexpr int PREP_THREADS = 96;
+constexpr int PREP_SCAN_THREADS = 256;  // block size when the epoch scan rides on the prep kernel
 
-__global__ void __launch_bounds__(PREP_THREADS)
+// optional fused epoch scan (transit_epoch_scan_kernel's work for this walker, by the same CTA).  The
+// counter must be zero when the kernel starts: the finalize / diag kernel of the evaluation resets it.
+struct PrepScan {
+	int enabled;
+	unsigned long long *queue;
+	unsigned int *qcount;
+};
+__device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
+				  unsigned int *qcount);
+
+__global__ void __launch_bounds__(PREP_SCAN_THREADS)
 prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep, int *flags,
-	    PrepReset R, PrepPropose PR)
+	    PrepReset R, PrepPropose PR, PrepScan SC)
 {
 	pdl_wait();
 	pdl_trigger();
@@ -363,6 +374,11 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 		pp[PP_TYPEMASK] = s_gp[3];
 		if (m.has_transit && pp[PP_WHALF] >= 0.5) fl |= WF_TR_ALL;
 		flags[gw] = fl;
+	}
+	if (SC.enabled) {
+		// the walker's window is complete (written by this CTA): queue its in-window samples right away
+		__syncthreads();
+		if (flags[gw] & WF_VALID) epoch_scan_walker(st, gw, pp, SC.queue, SC.qcount);
 	}
 }
 
@@ -573,18 +589,12 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 constexpr int EPOCH_SCAN_CAP = 6144;  // items gathered per flush (24 KB of shared memory)
 constexpr int SCAN_COARSE = 2048;     // entries of the coarse time table (16 KB of shared memory)
 
-__global__ void __launch_bounds__(TR_THREADS)
-transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
-			  unsigned int *qcount)
+// The scan of one walker by a whole CTA (any number of threads): shared by the stand-alone kernel and by
+// prep_kernel, which runs it right after it has written the walker's window.
+__device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
+				  unsigned int *qcount)
 {
-	pdl_wait();
-	pdl_trigger();
-	const int gw = blockIdx.x;
-	const int fl = flags[gw];
-	if (!(fl & WF_VALID)) return;
-	const StarDev st = stars[gw / W];
 	const int N = st.N;
-	const double *pp = prep + (size_t)gw * PREP_STRIDE;
 	const double per = pp[PP_TR + 0], wcen = pp[PP_WCEN], whalf = pp[PP_WHALF], inv_per = pp[PP_INVPER];
 	const double *t = st.tdays;
 	if (whalf < 0.0) return;  // never in transit
@@ -734,6 +744,20 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 			if (in_transit_window(t[n], wcen, inv_per, whalf))
 				queue[base++] = ((unsigned long long)(unsigned)gw << 32) | (unsigned)n;
 	}
+}
+
+
+__global__ void __launch_bounds__(TR_THREADS)
+transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
+			  unsigned int *qcount)
+{
+	pdl_wait();
+	pdl_trigger();
+	const int gw = blockIdx.x;
+	const int fl = flags[gw];
+	if (!(fl & WF_VALID)) return;
+	const StarDev st = stars[gw / W];
+	epoch_scan_walker(st, gw, prep + (size_t)gw * PREP_STRIDE, queue, qcount);
 }
 
 #ifndef TR_MINBLOCKS
@@ -1514,6 +1538,7 @@ struct FinalArgs {
 	unsigned long long *acc;  // [2] running totals over calls: flagged chunks, max error ratio (bits)
 	int *wbad;      // [nwalk] 1: the walker had a flagged chunk (its result is final only after pass 2)
 	double tol;
+	unsigned int *qreset;  // fused-scan item counter: [1] = [0], [0] = 0 for the next evaluation (or null)
 	FinalAccept AC;
 };
 
@@ -1613,6 +1638,10 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 	if (acc_warp) sampler_accept_prefetch(A.AC.S, A.AC.step, A.AC.half, gw, lane, pre);
 	pdl_wait();
 	pdl_trigger();
+	if (gw == 0 && tid == 0 && A.qreset && !A.skip_if_clean) {
+		A.qreset[1] = A.qreset[0];
+		A.qreset[0] = 0;
+	}
 	if (A.skip_if_clean && (*A.nbad == 0 || !A.wbad[gw])) return;  // second invocation: flagged walkers only
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
@@ -1859,12 +1888,17 @@ struct DiagArgs {
 	const double *mean;
 	double *lp, *parts;
 	int W, nwalk, N, gp, transit, has_err;
+	unsigned int *qreset;  // as FinalArgs::qreset
 };
 
 __global__ void diag_kernel(DiagArgs A)
 {
 	pdl_wait();
 	pdl_trigger();
+	if (blockIdx.x == 0 && threadIdx.x == 0 && A.qreset) {
+		A.qreset[1] = A.qreset[0];
+		A.qreset[0] = 0;
+	}
 	const int lane = threadIdx.x & 31;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= A.nwalk) return;
