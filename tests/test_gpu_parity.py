@@ -648,3 +648,34 @@ def test_regular_step_treatments_agree(engine, jitter):
     finally:
         engine.set_option("series_order_min", 0)
         engine.set_option("chunks", 0)
+
+
+@pytest.mark.parametrize("bmax", [300.0, 700.0, 1500.0, 4000.0])
+def test_fast_decay_shortens_the_scaled_runs(engine, bmax):
+    """The scaled state divides by s = exp(-c (x - x_anchor)); a mode that decays fast (large granulation
+    frequency: c dt0 up to ~30 here) forces shorter runs between re-anchorings (128 -> 8 steps) and, past
+    that, the general loop.  Every run length must reproduce the oracle."""
+    t, y, yerr = synthetic_star(5000, 9)
+    gp_cfg = [
+        {"type": "granulation", "params": {"values": {"a_gran": [False, None, "uniform", 100, 400],
+                                                      "b_gran": [False, None, "uniform", 0.5 * bmax, bmax]}}},
+        {"type": "granulation", "params": {"values": {"a_gran": [False, None, "uniform", 75, 225],
+                                                      "b_gran": [False, None, "uniform", 7.5, 22.5]}}},
+        {"type": "white_noise", "params": {"values": {"jitter": [False, None, "uniform", 50, 150]}}},
+    ]
+    np.random.seed(12)
+    gp = GPModel(gp_cfg)
+    spec = build_spec(gp, None)
+    theta = gp.sample_prior(32)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    assert np.all(np.isfinite(want_lp))
+    try:
+        for chunks in (1, 5, 0):
+            engine.set_option("chunks", chunks)
+            lp, parts = engine.log_prob(theta, return_parts=True)
+            assert_parts_close(parts, want)
+    finally:
+        engine.set_option("chunks", 0)
