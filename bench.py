@@ -418,6 +418,8 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
                          "peak_source": "measured on this GPU by gpt_measure_fp64_peak (DFMA kernel); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
+                         "frac_counting_halo_steps": ((achieved_tf / peak_tf) * (1.0 + (stats["halo"] / stats["chunk_len"]
+                                                      if stats["chunks"] > 1 else 0.0))) if achieved_tf else None,
                          "flops_per_launch": flops_per_launch, "kernel_ms": chunk_ms / max(chunk_n, 1),
                          "kernel_launches_timed": chunk_n, "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
                          "hbm_algorithmic_bytes_per_launch": bytes_per_launch, "traffic": traffic,

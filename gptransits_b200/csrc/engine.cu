@@ -347,6 +347,10 @@ static int chunk_threads(int W) { return std::min(CHUNK_THREADS, ((W + 31) / 32)
 
 static void launch_finalize(int nt, int nwalk, cudaStream_t st, const FinalArgs &f)
 {
+	if (f.nchunks == 1 && !f.skip_if_clean) {
+		launch_k(gp_finalize_wide_kernel, dim3((nwalk + FINW_THREADS / 32 - 1) / (FINW_THREADS / 32)), dim3(FINW_THREADS), 0, st, f);
+		return;
+	}
 	switch (nt) {
 	case 1: launch_k(gp_finalize_kernel<1>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
 	case 2: launch_k(gp_finalize_kernel<2>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
@@ -415,7 +419,14 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	}
 
 	// small batches: the epoch scan rides on the prep kernel (one launch, the window never leaves the CTA)
-	const bool fuse_scan = m.has_transit && nwalk <= 4096 && e->opt_epoch_scan && e->opt_fuse_scan;
+	const bool fuse_scan = m.has_transit && nwalk <= 1024 && e->opt_epoch_scan && e->opt_fuse_scan;
+	int prep_threads = PREP_THREADS;
+	if (fuse_scan) {
+		// one thread per transit epoch: a few per 256 samples at most for any realistic period
+		int et = 32;
+		while (et < PREP_SCAN_THREADS && et * 256 < N) et *= 2;
+		prep_threads = std::max(PREP_THREADS, et);
+	}
 	if (fuse_scan && !e->d_qfused.p) {
 		CK(e->d_qfused.ensure(2));
 		CK(cudaMemsetAsync(e->d_qfused.p, 0, 2 * sizeof(unsigned int), st));
@@ -434,7 +445,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	sc.queue = e->d_queue.p;
 	sc.qcount = qcount;
 	if (nwalk <= 4096)
-		launch_k(prep_kernel, dim3(nwalk), dim3(fuse_scan ? PREP_SCAN_THREADS : PREP_THREADS), 0, st, m, dst, W, d_theta, nwalk,
+		launch_k(prep_kernel, dim3(nwalk), dim3(prep_threads), 0, st, m, dst, W, d_theta, nwalk,
 			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	else
 		launch_k(prep_wide_kernel, dim3((nwalk + 63) / 64), dim3(64), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);

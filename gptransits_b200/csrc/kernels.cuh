@@ -1778,6 +1778,51 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 	}
 }
 
+// The same for evaluations that were not cut in time (nchunks == 1: many stars, short light curves): no
+// boundary to verify, one partial per walker -- one warp per walker, eight walkers per CTA.
+constexpr int FINW_THREADS = 256;
+__global__ void __launch_bounds__(FINW_THREADS) gp_finalize_wide_kernel(FinalArgs A)
+{
+	const int lane = threadIdx.x & 31;
+	const int gw = blockIdx.x * (FINW_THREADS / 32) + (threadIdx.x >> 5);
+	AcceptPre pre;
+	if (gw < A.nwalk && A.AC.enabled) sampler_accept_prefetch(A.AC.S, A.AC.step, A.AC.half, gw, lane, pre);
+	pdl_wait();
+	pdl_trigger();
+	if (blockIdx.x == 0 && threadIdx.x == 0 && A.qreset) {
+		A.qreset[1] = A.qreset[0];
+		A.qreset[0] = 0;
+	}
+	if (gw >= A.nwalk) return;
+	const int fl = A.flags[gw];
+	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
+	if ((fl & WF_VALID) && (fl & WF_GENERIC)) return;  // written by gp_generic_kernel
+	double lp = -CUDART_INF, lnl = -CUDART_INF, quad = CUDART_NAN, logdet = CUDART_NAN;
+	const double lnprior = pp[PP_LNPRIOR];
+	if (fl & WF_VALID) {
+		const ChunkPartial pr = A.partial[gw];
+		quad = pr.quad;
+		logdet = pr.logdet;
+		lnl = -0.5 * (quad + logdet + (double)A.N * 1.8378770664093454836);
+		lp = lnprior + lnl;
+		if ((A.wstatus[gw] & WF_NOTPD) || !isfinite(logdet) || !isfinite(lnl)) {
+			lp = -CUDART_INF;
+			lnl = -CUDART_INF;
+		}
+	}
+	if (lane == 0) {
+		if (A.wbad) A.wbad[gw] = 0;
+		A.lp[gw] = lp;
+		if (A.parts) {
+			A.parts[4 * gw + 0] = lnprior;
+			A.parts[4 * gw + 1] = quad;
+			A.parts[4 * gw + 2] = logdet;
+			A.parts[4 * gw + 3] = (fl & WF_VALID) ? lnl : CUDART_NAN;
+		}
+	}
+	if (A.AC.enabled) sampler_accept_commit(A.AC.S, pre, gw, lp, A.AC.slot, lane);
+}
+
 // ================================================================== generic (Q < 1/2) kernel
 // celerite's algorithm with per-column phi, sequential in time, one thread per flagged walker.
 struct GenericArgs {
