@@ -330,6 +330,18 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 	launch_kx(true, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
+// dynamic shared memory of the epoch scan (stand-alone or fused into the prep kernel) for light curves of N
+// samples: the coarse time table and room for the walker's items -- an eighth of the light curve covers any
+// realistic transit duty cycle (a walker that needs more takes the direct-append path)
+static int scan_items_cap(int N) { return std::max(256, std::min(EPOCH_SCAN_CAP, N / 8)); }
+static size_t scan_smem_bytes(int N)
+{
+	int cstride = TILE;
+	while ((N + cstride - 1) / cstride > SCAN_COARSE) cstride <<= 1;
+	const int ncoarse = (N + cstride - 1) / cstride;
+	return sizeof(double) * (size_t)ncoarse + sizeof(unsigned int) * (size_t)scan_items_cap(N);
+}
+
 // flux of the queued (walker, sample) items; "transit_strict" selects batman's own operation order
 static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *stars, int W, int ss, double exp_time,
 				int mode, const double *prep, const unsigned long long *queue, const unsigned int *qcount,
@@ -442,10 +454,11 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	if (propose) pr = *propose;
 	PrepScan sc;
 	sc.enabled = fuse_scan ? 1 : 0;
+	sc.items_cap = scan_items_cap(N);
 	sc.queue = e->d_queue.p;
 	sc.qcount = qcount;
 	if (nwalk <= 4096)
-		launch_k(prep_kernel, dim3(nwalk), dim3(prep_threads), 0, st, m, dst, W, d_theta, nwalk,
+		launch_k(prep_kernel, dim3(nwalk), dim3(prep_threads), fuse_scan ? scan_smem_bytes(N) : 0, st, m, dst, W, d_theta, nwalk,
 			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	else
 		launch_k(prep_wide_kernel, dim3((nwalk + 63) / 64), dim3(64), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
@@ -460,7 +473,8 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 				// one thread per transit epoch: a few per 256 samples at most for any realistic period
 				int et = 32;
 				while (et < TR_THREADS && et * 256 < N) et *= 2;
-				launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, qcount);
+				launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), scan_smem_bytes(N), st, dst, W, e->d_prep.p, e->d_flags.p,
+					 e->d_queue.p, qcount, scan_items_cap(N));
 			} else {
 				launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, qcount,
 					 e->d_mean.p, 0);

@@ -218,11 +218,12 @@ constexpr int PREP_SCAN_THREADS = 256;  // block size when the epoch scan rides 
 // counter must be zero when the kernel starts: the finalize / diag kernel of the evaluation resets it.
 struct PrepScan {
 	int enabled;
+	int items_cap;
 	unsigned long long *queue;
 	unsigned int *qcount;
 };
 __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
-				  unsigned int *qcount);
+				  unsigned int *qcount, int items_cap);
 
 __global__ void __launch_bounds__(PREP_SCAN_THREADS)
 prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep, int *flags,
@@ -378,7 +379,7 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 	if (SC.enabled) {
 		// the walker's window is complete (written by this CTA): queue its in-window samples right away
 		__syncthreads();
-		if (flags[gw] & WF_VALID) epoch_scan_walker(st, gw, pp, SC.queue, SC.qcount);
+		if (flags[gw] & WF_VALID) epoch_scan_walker(st, gw, pp, SC.queue, SC.qcount, SC.items_cap);
 	}
 }
 
@@ -586,13 +587,16 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 // then applies the SAME per-sample test as the consumers to the few candidates, so the queue holds
 // exactly the samples for which the GP kernels will read mean[].  Walkers whose window covers
 // everything are swept by the whole CTA.
-constexpr int EPOCH_SCAN_CAP = 6144;  // items gathered per flush (24 KB of shared memory)
+constexpr int EPOCH_SCAN_CAP = 6144;  // most items gathered per flush (24 KB of shared memory)
 constexpr int SCAN_COARSE = 2048;     // entries of the coarse time table (16 KB of shared memory)
 
 // The scan of one walker by a whole CTA (any number of threads): shared by the stand-alone kernel and by
 // prep_kernel, which runs it right after it has written the walker's window.
+// Dynamic shared memory of the launching kernel: [coarse table: min(SCAN_COARSE, ceil(N / TILE)) doubles]
+// [items_cap unsigned ints] -- sized by the host (scan_smem_bytes) so that short light curves keep many CTAs
+// resident.
 __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
-				  unsigned int *qcount)
+				  unsigned int *qcount, int items_cap)
 {
 	const int N = st.N;
 	const double per = pp[PP_TR + 0], wcen = pp[PP_WCEN], whalf = pp[PP_WHALF], inv_per = pp[PP_INVPER];
@@ -621,12 +625,13 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 	const long long kmin = (long long)kminf, kmax = (long long)kmaxf;
 	// The walker's items are gathered in shared memory and appended to the global queue with ONE
 	// atomic per flush (a single global counter cannot take tens of thousands of atomics per launch).
-	__shared__ unsigned int s_items[EPOCH_SCAN_CAP];
-	__shared__ double s_coarse[SCAN_COARSE];  // every cstride-th sample time: the search starts in shared memory
+	extern __shared__ __align__(16) unsigned char s_scan_dyn[];
 	__shared__ unsigned int s_n, s_base;
 	int cstride = TILE;
 	while ((N + cstride - 1) / cstride > SCAN_COARSE) cstride <<= 1;
 	const int ncoarse = (N + cstride - 1) / cstride;
+	double *s_coarse = reinterpret_cast<double *>(s_scan_dyn);  // every cstride-th sample time: the search starts here
+	unsigned int *s_items = reinterpret_cast<unsigned int *>(s_coarse + ncoarse);
 	for (int i = threadIdx.x; i < ncoarse; i += blockDim.x) s_coarse[i] = t[(size_t)i * cstride];
 	if (threadIdx.x == 0) s_n = 0;
 	__syncthreads();
@@ -697,7 +702,7 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 			}
 		}
 		const unsigned int pos = cnt ? atomicAdd(&s_n, (unsigned int)cnt) : 0u;
-		const bool fits = pos + (unsigned int)cnt <= (unsigned int)EPOCH_SCAN_CAP;
+		const bool fits = pos + (unsigned int)cnt <= (unsigned int)items_cap;
 		if (cnt && fits) {
 			unsigned int q = pos;
 			while (mask) {
@@ -749,7 +754,7 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 
 __global__ void __launch_bounds__(TR_THREADS)
 transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
-			  unsigned int *qcount)
+			  unsigned int *qcount, int items_cap)
 {
 	pdl_wait();
 	pdl_trigger();
@@ -757,7 +762,7 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
 	const StarDev st = stars[gw / W];
-	epoch_scan_walker(st, gw, prep + (size_t)gw * PREP_STRIDE, queue, qcount);
+	epoch_scan_walker(st, gw, prep + (size_t)gw * PREP_STRIDE, queue, qcount, items_cap);
 }
 
 #ifndef TR_MINBLOCKS

@@ -679,3 +679,35 @@ def test_fast_decay_shortens_the_scaled_runs(engine, bmax):
             assert_parts_close(parts, want)
     finally:
         engine.set_option("chunks", 0)
+
+
+def test_long_transits_overflow_the_scan_buffer(engine):
+    """Close-in orbits (a/R* of 1.2-2.5: a fifth to a third of all samples in transit) need more room than
+    the epoch scan's shared-memory buffer (an eighth of the light curve): the direct-append path of the
+    scan must queue exactly the same samples."""
+    t, y, yerr = synthetic_star(6000, 13)
+    tr_cfg = {"params": {"values": {
+        "P": [False, None, "uniform", 1.5, 4.0], "t0": [False, None, "uniform", 1.0, 2.0],
+        "Rrat": [False, None, "uniform", 0.02, 0.12], "aR": [False, None, "uniform", 1.2, 2.5],
+        "cosi": [False, None, "uniform", 80.0, 90.0],
+        "e": [True, 0.0, "uniform", 0, 1], "w": [True, 90.0, "uniform", 0, 90],
+        "u1": [True, 0.4996, "uniform", 0, 1], "u2": [True, 0.0847, "uniform", 0, 1]}}}
+    np.random.seed(23)
+    gp = GPModel(C3_CONFIG_GP)
+    tr = BatmanModel(tr_cfg)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    theta = np.hstack([gp.sample_prior(48), tr.sample_prior(48)])
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True, nthreads=8)
+    assert np.isfinite(want_lp).sum() >= 40
+    try:
+        for fuse in (1, 0):
+            engine.set_option("fuse_scan", fuse)
+            lp, parts = engine.log_prob(theta, return_parts=True)
+            assert_parts_close(parts, want)
+            assert engine.stat("transit_items") > 48 * 6000 / 8      # more than the buffers of all walkers hold
+    finally:
+        engine.set_option("fuse_scan", 1)
