@@ -336,7 +336,7 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 static int scan_items_cap(int N) { return std::max(256, std::min(EPOCH_SCAN_CAP, N / 8)); }
 static size_t scan_smem_bytes(int N)
 {
-	int cstride = TILE;
+	int cstride = SCAN_STRIDE;
 	while ((N + cstride - 1) / cstride > SCAN_COARSE) cstride <<= 1;
 	const int ncoarse = (N + cstride - 1) / cstride;
 	return sizeof(double) * (size_t)ncoarse + sizeof(unsigned int) * (size_t)scan_items_cap(N);

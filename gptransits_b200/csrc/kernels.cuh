@@ -94,7 +94,11 @@ __host__ __device__ constexpr int tri(int i, int j, int J)
 	return i * J - (i * (i - 1)) / 2 + (j - i);
 }
 
-constexpr int TILE = 128;     // samples per staged tile (4 KB)
+#ifndef GPT_TILE
+#define GPT_TILE 128
+#endif
+constexpr int TILE = GPT_TILE;  // samples per staged tile (32 bytes each); also the longest run between exact anchors
+constexpr int SCAN_STRIDE = 128;  // finest stride of the epoch scan's coarse time table
 constexpr int NSTAGE = 4;     // tiles in flight
 constexpr int CHUNK_THREADS = 128;
 
@@ -627,7 +631,7 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 	// atomic per flush (a single global counter cannot take tens of thousands of atomics per launch).
 	extern __shared__ __align__(16) unsigned char s_scan_dyn[];
 	__shared__ unsigned int s_n, s_base;
-	int cstride = TILE;
+	int cstride = SCAN_STRIDE;
 	while ((N + cstride - 1) / cstride > SCAN_COARSE) cstride <<= 1;
 	const int ncoarse = (N + cstride - 1) / cstride;
 	double *s_coarse = reinterpret_cast<double *>(s_scan_dyn);  // every cstride-th sample time: the search starts here
