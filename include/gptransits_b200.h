@@ -83,8 +83,14 @@ void gpt_engine_destroy(gpt_engine *e);
 const char *gpt_last_error(const gpt_engine *e);
 const char *gpt_version(void);
 
-/* Tunables ("halo", "chunks", "verify", "tile", ...) and counters
- * ("launches", "pass2_chunks", "halo", "chunks", "last_kernel_ms", ...). */
+/* Tunables: "halo" (fixed halo length, 0 = adaptive), "chunks" (0 = cost model), "verify", "verify_tol",
+ * "halo_auto", "adapt_every" (sampler steps per block), "ctas_per_sm", "min_chunk_halos", "epoch_scan",
+ * "fuse_scan" (epoch scan inside the prep kernel for small batches, default 1), "transit_strict" (batman's
+ * operation order), "series_order_min" (0..4: lowest treatment of regular-cadence steps, 4 = general loop),
+ * "pdl" (programmatic dependent launch, default 0), "speculate" (sampler blocks without repair launches,
+ * replayed when a chunk was flagged, default 0), "time_kernels", "reset_timers".
+ * Counters: "launches", "evals", "pass2_chunks", "spec_replays", "verify_ratio", "halo", "chunks", "chunk_len",
+ * "transit_items", "ms_<kernel>" / "n_<kernel>" for prep, transit, trscan, chunk, final, pass2. */
 int gpt_set_option(gpt_engine *e, const char *key, double value);
 int gpt_get_stat(gpt_engine *e, const char *key, double *value);
 
