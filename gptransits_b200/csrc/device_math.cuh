@@ -324,6 +324,24 @@ __device__ __forceinline__ double rcp_nr(double d)
 	return fma(r, e, r);
 }
 
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	const double h = 0.5 * x;
+	double e = fma(-h * y, y, 0.5);
+	y = fma(y, e, y);
+	e = fma(-h * y, y, 0.5);
+	return fma(y, e, y);
+}
+// sqrt(x) for finite x without the library routine's slow-path branch: x * rsqrt(x), <= 2 ulp
+// (0 -> 0, negative or NaN -> NaN)
+__device__ __forceinline__ double sqrt_nr(double x)
+{
+	const double r = x * rsqrt_nr(x);
+	return x == 0.0 ? 0.0 : r;
+}
+
 __device__ inline void ellke_fast(double k, int mode, double &Kk, double &Ek, double &m1_out)
 {
 	m1_out = 1.0 - k * k;
@@ -346,7 +364,7 @@ __device__ inline void ellke_fast(double k, int mode, double &Kk, double &Ek, do
 // 1/p0 supplied by the caller (both are closed forms of the geometry, no square root needed)
 __device__ inline double ellpic_fast(double kc2, double p0, double rp0, double tol)
 {
-	double kc = sqrt(kc2);
+	double kc = sqrt_nr(kc2);
 	double p = p0;
 	double m0 = 1., c = 1., d = rp0, e = kc, f, g;
 	for (int nit = 0; nit < 10000; nit++) {
@@ -359,7 +377,7 @@ __device__ inline double ellpic_fast(double kc2, double p0, double rp0, double t
 		g = m0;
 		m0 = kc + m0;
 		if (fabs(g - kc) > tol * g) {
-			kc = 2. * sqrt(e);
+			kc = 2. * sqrt_nr(e);
 			e = kc * m0;
 		} else {
 			return 0.5 * kPi * fma(c, m0, d) * rcp_nr(m0 * (m0 + p));
@@ -368,16 +386,6 @@ __device__ inline double ellpic_fast(double kc2, double p0, double rp0, double t
 	return 0.0;
 }
 
-__device__ __forceinline__ double rsqrt_nr(double x)
-{
-	double y;
-	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-	const double h = 0.5 * x;
-	double e = fma(-h * y, y, 0.5);
-	y = fma(y, e, y);
-	e = fma(-h * y, y, 0.5);
-	return fma(y, e, y);
-}
 
 // rp_inv = 1/p, inv_omega = 1/(1 - c1/3 - c2/6): per-walker constants.
 // Structure: the case analysis only selects coefficients (q^2, n, prefactor, cK, cE, cP, lambda_e,
@@ -470,7 +478,7 @@ __device__ inline double ma_flux_fast(double d, double p, double rp_inv, double 
 	}
 	// converged part: every lane of the warp that needs K, E, Pi computes them here together
 	if (elliptic) {
-		const double q = sqrt(q2);
+		const double q = sqrt_nr(q2);
 		double Kk, Ek, m1;
 		ellke_fast(q, mode, Kk, Ek, m1);
 		const double Pk = ellpic_fast(m1, ep0, erp0, pitol);
@@ -548,7 +556,7 @@ __device__ inline double rsky_fast(double t, const TransitPars &tr)
 		sf = sin(tr.w + f);
 		r = tr.a * (1.0 - tr.ecc * tr.ecc) / (1.0 + tr.ecc * cos(f));
 	}
-	const double d = r * sqrt(1.0 - sf * sf * si * si);
+	const double d = r * sqrt_nr(1.0 - sf * sf * si * si);
 	return (si * sf > 0.) ? d : 100.;
 }
 
