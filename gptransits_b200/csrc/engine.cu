@@ -1371,6 +1371,82 @@ int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat)
 	return GPT_OK;
 }
 
+// ---- single star, ensemble sharded by walker across ranks (one process per GPU) ------------------
+// Every rank holds the whole ensemble.  A half-step is: gpt_sampler_half_eval (proposals of all active
+// walkers; log-probabilities of this rank's slice [lo, hi) of them into lq) -> all-gather of lq by the
+// caller (NCCL on the device pointer gpt_sampler_lq_device returns) -> gpt_sampler_half_accept (identical
+// accept/reject on every rank: the replicated state never diverges).
+int gpt_sampler_reserve(gpt_engine *e, int64_t nsteps)
+{
+	if (!e || !e->sampling || nsteps < 0) return GPT_E_INVALID;
+	cudaSetDevice(e->device);
+	SamplerDev &S = e->S;
+	const size_t nw = (size_t)S.nstars * S.W;
+	CK(e->s_chain.ensure(nw * std::max<int64_t>(nsteps, 1) * S.ndim));
+	CK(e->s_logp.ensure(nw * std::max<int64_t>(nsteps, 1)));
+	S.chain = e->s_chain.p;
+	S.logp = e->s_logp.p;
+	S.cap = nsteps;
+	e->s_kept = 0;
+	return GPT_OK;
+}
+
+int gpt_sampler_lq_device(gpt_engine *e, void **lq, int64_t *count)
+{
+	if (!e || !e->sampling || !lq || !count) return GPT_E_INVALID;
+	*lq = e->S.lq;
+	*count = (int64_t)e->S.nstars * (e->S.W / 2);
+	return GPT_OK;
+}
+
+int gpt_sampler_half_eval(gpt_engine *e, int half, int lo, int hi)
+{
+	if (!e || !e->sampling || half < 0 || half > 1) return GPT_E_INVALID;
+	SamplerDev &S = e->S;
+	const int H = S.W / 2;
+	if (S.nstars != 1 || lo < 0 || hi > H || lo > hi) {
+		e->set_error("sampler_half_eval: one star, 0 <= lo <= hi <= W/2");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	cudaStream_t st = e->stream;
+	if (half == 0) {
+		CK(e->s_act.ensure((size_t)S.W));
+		S.act = e->s_act.p;
+		launch_k(sampler_split_kernel, dim3(1, 1), dim3(256), (size_t)S.W * (sizeof(unsigned long long) + sizeof(int)), st, S, e->s_step);
+		e->n_launch++;
+	}
+	launch_k(sampler_propose_kernel, dim3((H + 127) / 128), dim3(128), 0, st, S, e->s_step, half);
+	e->n_launch++;
+	if (hi > lo) {
+		int rc = eval_enqueue(e, e->s_star0, 1, S.q + (size_t)lo * S.ndim, hi - lo, S.lq + lo, nullptr, false);
+		if (rc) return rc;
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));  // the caller's collective runs on its own stream
+	return GPT_OK;
+}
+
+int gpt_sampler_half_accept(gpt_engine *e, int half, int keep)
+{
+	if (!e || !e->sampling || half < 0 || half > 1) return GPT_E_INVALID;
+	SamplerDev &S = e->S;
+	if (keep && (!S.chain || e->s_kept >= S.cap)) {
+		e->set_error("sampler_half_accept: gpt_sampler_reserve first (chain full)");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	const int nh = S.nstars * (S.W / 2);
+	launch_k(sampler_accept_kernel, dim3((nh + 127) / 128), dim3(128), 0, e->stream, S, e->s_step, half, keep ? e->s_kept : -1LL);
+	e->n_launch++;
+	if (half == 1) {
+		if (keep) e->s_kept++;
+		e->s_step++;
+	}
+	CK(cudaGetLastError());
+	return GPT_OK;
+}
+
 int gpt_sampler_end(gpt_engine *e)
 {
 	if (!e) return GPT_E_INVALID;

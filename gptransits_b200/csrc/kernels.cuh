@@ -2210,6 +2210,17 @@ __global__ void sampler_split_kernel(SamplerDev S, unsigned long long step0)
 	}
 }
 
+// standalone stretch proposals of every active walker (walker-sharded multi-GPU half-step: each rank
+// proposes for the whole half and evaluates only its slice)
+__global__ void sampler_propose_kernel(SamplerDev S, unsigned long long step, int half)
+{
+	pdl_wait();
+	pdl_trigger();
+	const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gi >= S.nstars * (S.W / 2)) return;
+	sampler_propose_one(S, step, half, gi);
+}
+
 // standalone accept/reject (models whose log-probability is not produced by gp_finalize_kernel)
 __global__ void sampler_accept_kernel(SamplerDev S, unsigned long long step, int half, long long slot)
 {

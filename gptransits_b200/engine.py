@@ -182,6 +182,22 @@ class Engine:
     def sampler_end(self):
         self._ck(self._lib.gpt_sampler_end(self._h))
 
+    # -- one star sharded by walker across ranks (parallel.run_walker_sharded)
+    def sampler_reserve(self, nsteps):
+        self._ck(self._lib.gpt_sampler_reserve(self._h, int(nsteps)))
+
+    def sampler_lq_device(self):
+        """(device pointer, count) of the proposal log-probabilities lq[W/2] of the current half-step."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(self._lib.gpt_sampler_lq_device(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def sampler_half_eval(self, half, lo, hi):
+        self._ck(self._lib.gpt_sampler_half_eval(self._h, int(half), int(lo), int(hi)))
+
+    def sampler_half_accept(self, half, keep=True):
+        self._ck(self._lib.gpt_sampler_half_accept(self._h, int(half), 1 if keep else 0))
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         self._ck(self._lib.gpt_measure_fp64_peak(self._h, C.byref(v)))

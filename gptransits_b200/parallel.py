@@ -42,6 +42,55 @@ def run_star_sharded(engine, t, ys, yerr, init, nsteps, seed, rank, world):
     return lo, hi, chain, logp
 
 
+class _DeviceArray:
+    """Zero-copy view of engine-owned device memory for torch (``torch.as_tensor(_DeviceArray(...))``)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def run_walker_sharded(engine, dist, init, nsteps, seed=42, step0=0, a=2.0):
+    """One star, the ensemble sharded by walker across the ranks of `dist` (NCCL, one process per GPU).
+
+    The device-resident form of SURVEY.md section 8e(2): every rank keeps the whole ensemble on its GPU;
+    per half-step it proposes for all active walkers, evaluates its slice of them, the slices of the
+    proposal log-probabilities are all-gathered in place on the device (the only collective, twice per
+    step, a few hundred bytes) and every rank applies the identical accept/reject.  The star must already
+    be uploaded (slot 0) on every rank.  Returns (chain[W, nsteps, ndim], logp[nsteps, W]) -- the same
+    on every rank and, up to the evaluation geometry's rounding, the single-GPU sampler's."""
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    init = np.asarray(init, dtype=float)
+    W = init.shape[0]
+    H = W // 2
+    engine.sampler_begin(init, seed=seed, step0=step0, a=a, nstars=1)
+    try:
+        engine.sampler_reserve(nsteps)
+        if world > 1:
+            import torch
+            ptr, count = engine.sampler_lq_device()
+            lq = torch.as_tensor(_DeviceArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+        slices = [walker_slice(H, r, world) for r in range(world)]
+        lo, hi = slices[rank]
+        even = H % world == 0
+        for _ in range(nsteps):
+            for half in (0, 1):
+                engine.sampler_half_eval(half, lo, hi)          # returns with the engine's stream drained
+                if world > 1:
+                    if even:
+                        dist.all_gather_into_tensor(lq, lq[lo:hi].clone())
+                    else:
+                        for r, (l, h) in enumerate(slices):
+                            if h > l:
+                                dist.broadcast(lq[l:h], src=r)
+                    torch.cuda.current_stream().synchronize()   # the accept runs on the engine's stream
+                engine.sampler_half_accept(half, keep=True)
+        chain, logp = engine.sampler_read(0, nsteps)
+    finally:
+        engine.sampler_end()
+    return chain[0], logp[0]
+
+
 def gather_chains(dist, local, nstars, rank, world):
     """All ranks -> rank 0: list of per-star arrays in global star order (host-side, once per run)."""
     out = [None] * world

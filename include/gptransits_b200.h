@@ -166,6 +166,16 @@ int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *nacc
  * kept steps [first, first + count) of the device chain, per star and parameter: rhat[nstars*ndim].
  * Replaces pulling the chain to the host for the check at model.py:417-424 while a run is in flight. */
 int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat);
+/* One star on several GPUs (one process each): the ensemble is sharded by walker.  Every rank
+ * holds the whole ensemble; per half-step: gpt_sampler_half_eval proposes for all active walkers and
+ * evaluates this rank's slice [lo, hi) of them into the device array lq[W/2] (gpt_sampler_lq_device), the
+ * caller all-gathers lq (ncclAllGather on that pointer -- the only collective of the path, twice per step),
+ * gpt_sampler_half_accept applies the same accept/reject on every rank.  gpt_sampler_reserve sizes the
+ * device chain first.  Replaces the pool hook of emcee's EnsembleSampler (model.py:269-270). */
+int gpt_sampler_reserve(gpt_engine *e, int64_t nsteps);
+int gpt_sampler_lq_device(gpt_engine *e, void **lq, int64_t *count);
+int gpt_sampler_half_eval(gpt_engine *e, int half, int lo, int hi);
+int gpt_sampler_half_accept(gpt_engine *e, int half, int keep);
 int gpt_sampler_end(gpt_engine *e);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------ */

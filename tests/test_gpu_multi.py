@@ -51,12 +51,15 @@ def _worker(rank, world, port, outdir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     t, y, yerr, spec, init = _setup()
     from gptransits_b200 import Engine
-    from gptransits_b200.parallel import HalfEnsembleSampler, run_star_sharded
+    from gptransits_b200.parallel import HalfEnsembleSampler, run_star_sharded, run_walker_sharded
     eng = Engine(rank)
     eng.set_model(spec)
     eng.upload_star(0, t, y, yerr)
     chain, logp = HalfEnsembleSampler(lambda th: eng.log_prob(th), init, seed=9, dist=dist).run(6)
     np.save(Path(outdir) / f"walker_{rank}.npy", chain)
+    # the device-resident form of the same protocol (C ABI half-step calls + NCCL all-gather in place)
+    dchain, dlogp = run_walker_sharded(eng, dist, init, 6, seed=9)
+    np.save(Path(outdir) / f"dwalker_{rank}.npy", dchain)
     # stars sharded by rank: 3 stars, global ids keep the RNG streams independent of the sharding
     ys = [y + 5.0 * s for s in range(3)]
     inits = np.stack([init] * 3)
@@ -81,6 +84,9 @@ def test_two_gpu_sharding(tmp_path):
     c0, c1 = np.load(tmp_path / "walker_0.npy"), np.load(tmp_path / "walker_1.npy")
     assert np.array_equal(c0, c1)
     assert np.max(np.abs(c0 - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
+    d0, d1 = np.load(tmp_path / "dwalker_0.npy"), np.load(tmp_path / "dwalker_1.npy")
+    assert np.array_equal(d0, d1)
+    assert np.max(np.abs(d0 - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
     got = {}
     for p in tmp_path.glob("stars_*.npy"):
         lo, hi = map(int, p.stem.split("_")[1:])

@@ -711,3 +711,24 @@ def test_long_transits_overflow_the_scan_buffer(engine):
             assert engine.stat("transit_items") > 48 * 6000 / 8      # more than the buffers of all walkers hold
     finally:
         engine.set_option("fuse_scan", 1)
+
+
+def test_walker_sharded_half_step_calls_reproduce_the_sampler(engine, sim_lc, sim_config):
+    """gpt_sampler_half_eval / gpt_sampler_half_accept (the walker-sharded multi-GPU protocol) with one rank
+    owning every walker must give the device sampler's chain (the log-probabilities up to the rounding of a
+    different halo length: the halo adapts between the two runs)."""
+    from gptransits_b200.parallel import run_walker_sharded
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config, "cosi")
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    np.random.seed(4)
+    W, nsteps = 24, 9
+    init = np.hstack([gp.sample_prior(W), tr.sample_prior(W)])
+    init[:, 9] = np.random.uniform(5, 15, W)
+    init[:, 10] = np.random.uniform(0, 0.05, W)
+    want, wlogp, _ = engine.sample(init, nsteps, seed=21)
+    chain, logp = run_walker_sharded(engine, None, init, nsteps, seed=21)
+    assert np.array_equal(chain, want)
+    fin = np.isfinite(wlogp)
+    assert np.array_equal(np.isfinite(logp), fin) and rel(logp[fin], wlogp[fin]) < 1e-9
