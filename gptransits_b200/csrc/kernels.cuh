@@ -670,6 +670,79 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 	};
 	const long long nk = kmax - kmin + 1;
 	const long long rounds = (nk + blockDim.x - 1) / blockDim.x;
+	if (2.0 * whalf * pa > 32.0 * dt_med && blockDim.x <= PREP_SCAN_THREADS) {
+		// Long windows (tens of samples or more per epoch: short cadence): a thread per epoch walking its
+		// window alone would serialise it.  Each thread only brackets its epoch, [a, b) = samples with
+		// lo <= t <= hi; the candidates of all epochs of the round are then laid end to end and tested by the
+		// whole CTA, items_cap at a time, each pass appended to the global queue with one atomic.
+		__shared__ int s_a[PREP_SCAN_THREADS], s_off[PREP_SCAN_THREADS + 1];
+		const int tid = threadIdx.x, nthr = blockDim.x;
+		for (long long rd = 0; rd < rounds; rd++) {
+			const long long k = kmin + rd * nthr + tid;
+			int a = 0, cnt = 0;
+			if (k <= kmax) {
+				const double tc = wcen + (double)k * pa;
+				const double half = whalf * pa;
+				const double eps = 1e-9 * pa + 1e-12 * fabs(tc);
+				const double lo = tc - half - eps, hi = tc + half + eps;
+				if (!(hi < t[0] || lo > t[N - 1])) {
+					a = lower_bound(lo);
+					int b = lower_bound(hi);        // first t >= hi ...
+					while (b < N && t[b] <= hi) b++;  // ... then past the samples equal to hi
+					cnt = max(b - a, 0);
+				}
+			}
+			// exclusive scan of cnt over the CTA (Hillis-Steele in shared memory)
+			s_a[tid] = a;
+			s_off[tid + 1] = cnt;
+			if (tid == 0) s_off[0] = 0;
+			__syncthreads();
+			for (int d = 1; d < nthr; d <<= 1) {
+				const int v = tid + 1 > d ? s_off[tid + 1 - d] : 0;
+				__syncthreads();
+				if (tid + 1 > d) s_off[tid + 1] += v;
+				__syncthreads();
+			}
+			const int total = s_off[nthr];
+			for (int f0 = 0; f0 < total; f0 += items_cap) {
+				const int f1 = min(total, f0 + items_cap);
+				if (tid == 0) s_n = 0;
+				__syncthreads();
+				for (int fb = f0; fb < f1; fb += nthr) {
+					const int f = fb + tid;
+					bool inw = false;
+					int n = 0;
+					if (f < f1) {
+						int ea = 0, eb = nthr;  // last epoch e with s_off[e] <= f
+						while (eb - ea > 1) {
+							const int md = (ea + eb) >> 1;
+							if (s_off[md] <= f) ea = md; else eb = md;
+						}
+						n = s_a[ea] + (f - s_off[ea]);
+						inw = in_transit_window(t[n], wcen, inv_per, whalf);
+					}
+					const unsigned mask = __ballot_sync(0xffffffffu, inw);
+					if (mask) {
+						const int lane = tid & 31, leader = __ffs(mask) - 1;
+						unsigned int base = 0;
+						if (lane == leader) base = atomicAdd(&s_n, (unsigned int)__popc(mask));
+						base = __shfl_sync(0xffffffffu, base, leader);
+						if (inw) s_items[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)n;
+					}
+				}
+				__syncthreads();
+				const unsigned int have = s_n;
+				if (have) {
+					if (tid == 0) s_base = atomicAdd(qcount, have);
+					__syncthreads();
+					for (unsigned int i = tid; i < have; i += nthr)
+						queue[s_base + i] = ((unsigned long long)(unsigned)gw << 32) | s_items[i];
+				}
+				__syncthreads();
+			}
+		}
+		return;
+	}
 	bool overflow = false;
 	for (long long rd = 0; rd < rounds; rd++) {
 		const long long k = kmin + rd * blockDim.x + threadIdx.x;
