@@ -85,8 +85,10 @@ struct gpt_engine {
 	int opt_adapt_every = 32;  // sampler steps between halo adaptations
 	int opt_transit_strict = 0;
 	int opt_series_order_min = 0;
-	int opt_speculate = 0;   // speculative sampler blocks (no repair launches, replay on a flagged chunk): see sampler_run_impl
-	int spec_clean = 2;  // consecutive clean blocks; a block runs speculatively after two (a flagged one resets it)
+	int opt_speculate = 1;   // speculative sampler blocks: 0 never, 1 after a long clean record, 2 whenever the last block was clean
+	long long spec_clean_steps = 0;   // sampler steps since a chunk was last flagged (or the halo last changed)
+	long long spec_need_steps = 128;  // clean record needed before a block runs speculatively; doubles on a replay
+	bool spec_last_clean = true;
 	long long n_spec_replays = 0;
 	int opt_ctas_per_sm = 1;
 	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
@@ -628,6 +630,7 @@ int gpt_star_clear(gpt_engine *e)
 		if (s.blob) cudaFree(s.blob);
 	e->stars.clear();
 	e->stars_dirty = true;
+	e->spec_clean_steps = 0;  // new data: the clean record of the speculative sampler starts over
 	return GPT_OK;
 }
 
@@ -675,7 +678,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 	} else if (k == "fuse_scan") {
 		e->opt_fuse_scan = value != 0;
 	} else if (k == "speculate") {
-		e->opt_speculate = value != 0;
+		e->opt_speculate = std::min(2, std::max(0, (int)value));
+		e->spec_last_clean = true;
 	} else if (k == "pdl") {
 		g_pdl = value != 0;
 	} else if (k == "adapt_every") {
@@ -839,6 +843,9 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *d)
 		e->cur_halo = 0;
 		e->fail_halo = 0;
 		e->fail_age = 0;
+		e->spec_clean_steps = 0;
+		e->spec_need_steps = 128;
+		e->spec_last_clean = true;
 	}
 	e->model = m;
 	e->may_generic = may_generic;
@@ -969,6 +976,7 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	CK(cudaMemcpyAsync(s.blob, e->h_stage, total, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	e->stars_dirty = true;
+	e->spec_clean_steps = 0;  // new data: the clean record of the speculative sampler starts over
 	return GPT_OK;
 }
 
@@ -1091,7 +1099,6 @@ int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	e->sampling = true;
-	e->spec_clean = 2;
 	return GPT_OK;
 }
 
@@ -1197,14 +1204,16 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 	};
 	if (ms_per_step)
 		for (int64_t s = 0; s < nsteps; s++) ms_per_step[s] = 0.f;
-	// Blocks of "adapt_every" steps.  With option "speculate" (off by default: the two idle repair launches
-	// per half-step cost only ~1 % of a C3 step, a replay costs a whole block, and light curves whose chunks
-	// are flagged now and then -- the bundled examples -- lose more than they gain) a block runs
-	// speculatively: no repair pass is enqueued, the chunk
-	// verification only accumulates its verdicts on the device.  They are read once per block (one small
+	// Blocks of "adapt_every" steps.  The two repair launches per half-step are idle as long as no chunk is
+	// flagged (C3: none in 3000 steps) and cost 3-4 % of a step, so once the sampler has a clean record of
+	// spec_need_steps steps at the current halo a block runs speculatively: no repair pass is enqueued, the
+	// chunk verification only accumulates its verdicts on the device.  They are read once per block (one small
 	// synchronisation, also used to steer the halo); if any chunk was flagged the ensemble is rolled back
 	// to the start of the block and the block is replayed with the repair pass -- the RNG is counter
-	// based, so the replay reproduces the same moves and the result does not depend on the speculation.
+	// based, so the replay reproduces the same moves and the result does not depend on the speculation --
+	// and the record needed doubles.  Light curves whose chunks are flagged now and then (the bundled
+	// examples) therefore never leave the repaired mode.  Option "speculate": 0 never, 1 this policy,
+	// 2 speculate whenever the previous block was clean (tests).
 	const bool can_speculate = e->opt_speculate && !e->may_generic && e->opt_verify;
 	const int64_t block = e->opt_adapt_every > 0 ? std::min(e->opt_adapt_every, 1024) : 64;
 	const size_t nw = (size_t)ns * W;
@@ -1212,7 +1221,9 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		const int64_t sb = std::min<int64_t>(nsteps, sa + block);
 		const unsigned long long step_at = e->s_step;
 		const long long kept_at = e->s_kept;
-		const bool spec = can_speculate && e->spec_clean >= 2;
+		const int halo_before = e->cur_halo;
+		const bool spec = can_speculate && (e->opt_speculate == 2 ? e->spec_last_clean
+									    : e->spec_clean_steps >= e->spec_need_steps);
 		if (spec) {
 			CK(e->s_snap_x.ensure(nw * ndim));
 			CK(e->s_snap_lpx.ensure(nw));
@@ -1228,11 +1239,12 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		if (rc) return rc;
 		rc = add_times(sa, sb);
 		if (rc) return rc;
-		// speculation pays only while flagged chunks are rare: after a block with one, blocks run with the
-		// repair pass enqueued (no replay possible) until two in a row come back clean
-		e->spec_clean = flagged ? 0 : std::min(e->spec_clean + 1, 2);
+		e->spec_last_clean = !flagged;
+		if (flagged || e->cur_halo != halo_before) e->spec_clean_steps = 0;
+		else e->spec_clean_steps += sb - sa;
 		if (spec && flagged) {
 			e->n_spec_replays++;
+			e->spec_need_steps = std::min<long long>(2 * e->spec_need_steps, 32768);
 			CK(cudaMemcpyAsync(S.x, e->s_snap_x.p, nw * ndim * sizeof(double), cudaMemcpyDeviceToDevice, st));
 			CK(cudaMemcpyAsync(S.lpx, e->s_snap_lpx.p, nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
 			CK(cudaMemcpyAsync(S.nacc, e->s_snap_nacc.p, nw * sizeof(long long), cudaMemcpyDeviceToDevice, st));

@@ -88,7 +88,7 @@ const char *gpt_version(void);
  * "fuse_scan" (epoch scan inside the prep kernel for small batches, default 1), "transit_strict" (batman's
  * operation order), "series_order_min" (0..4: lowest treatment of regular-cadence steps, 4 = general loop),
  * "pdl" (programmatic dependent launch, default 0), "speculate" (sampler blocks without repair launches,
- * replayed when a chunk was flagged, default 0), "time_kernels", "reset_timers".
+ * replayed when a chunk was flagged: 0 never, 1 after a long clean record -- default --, 2 eagerly), "time_kernels", "reset_timers".
  * Counters: "launches", "evals", "pass2_chunks", "spec_replays", "verify_ratio", "halo", "chunks", "chunk_len",
  * "transit_items", "ms_<kernel>" / "n_<kernel>" for prep, transit, trscan, chunk, final, pass2. */
 int gpt_set_option(gpt_engine *e, const char *key, double value);

@@ -600,7 +600,7 @@ def test_sampler_speculative_block_is_replayed_with_repair(engine):
     engine.set_option("chunks", 12)
     engine.set_option("halo", 2)
     engine.set_option("adapt_every", 3)          # blocks of 3, 3 and 1 steps
-    engine.set_option("speculate", 1)            # off by default
+    engine.set_option("speculate", 2)            # speculate whenever the previous block was clean
     try:
         before = engine.stat("spec_replays")
         chain, logp, nacc = engine.sample(init, nsteps, seed=77)
@@ -613,7 +613,7 @@ def test_sampler_speculative_block_is_replayed_with_repair(engine):
         chain2, logp2, nacc2 = engine.sample(init, nsteps, seed=77)
         assert np.array_equal(chain2, chain) and np.array_equal(logp2, logp) and np.array_equal(nacc2, nacc)
     finally:
-        engine.set_option("speculate", 0)
+        engine.set_option("speculate", 1)
         engine.set_option("adapt_every", 32)
         engine.set_option("chunks", 0)
         engine.set_option("halo", 0)
