@@ -497,6 +497,7 @@ struct TransitPars {
 	double tp;                                   // time of periastron (batman _rsky.c)
 	double wcen, whalf, inv_per;                 // conservative in-transit window
 	double sin_inc, rp_inv, inv_omega, w_over_pi; // per-walker constants of the throughput variant
+	bool inverse;                                // rp < 0: batman's inverse transit, light curve 2 - lc
 };
 
 __device__ inline double kepler_E(double M, double e)

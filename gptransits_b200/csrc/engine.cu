@@ -67,6 +67,8 @@ struct Star {
 
 struct gpt_engine {
 	int device = 0;
+	int num_sms = 148;       // cudaDevAttrMultiProcessorCount of the device (B200: 148)
+	double sm_clock_ghz = 0.0;  // cudaDevAttrClockRate
 	cudaStream_t stream = nullptr;
 	std::string err;
 	bool have_model = false;
@@ -279,7 +281,7 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 		// warps share the FP64 pipe at 1.21x the single-warp throughput, more warps queue up.
 		const int cthreads = std::min(CHUNK_THREADS, ((W + 31) / 32) * 32);
 		const double wpl = (double)nstars * ((W + cthreads - 1) / cthreads) * (cthreads / 32);  // warps per chunk layer
-		const double slots = 148.0 * 4.0;
+		const double slots = (double)e->num_sms * 4.0;
 		const int nc_max = std::max(1, N / 32);
 		double best = 1e300;
 		nc = 1;
@@ -349,7 +351,7 @@ static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *s
 				int mode, const double *prep, const unsigned long long *queue, const unsigned int *qcount,
 				double *out, int dense)
 {
-	const int grid = 148 * 2 * TR_MINBLOCKS;
+	const int grid = e->num_sms * 2 * TR_MINBLOCKS;
 	if (e->opt_transit_strict)
 		launch_k(transit_eval_kernel<true>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
 	else
@@ -609,6 +611,11 @@ int gpt_engine_create(int device, gpt_engine **out)
 	if (cudaSetDevice(device) != cudaSuccess) return GPT_E_CUDA;
 	gpt_engine *e = new gpt_engine();
 	e->device = device;
+	{
+		int v = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device) == cudaSuccess && v > 0) e->sm_clock_ghz = v * 1e-6;
+	}
 	if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaMallocHost((void **)&e->h_nbad, sizeof(int)) != cudaSuccess ||
 	    cudaMallocHost((void **)&e->h_verr, sizeof(double)) != cudaSuccess) {
@@ -723,6 +730,9 @@ int gpt_get_stat(gpt_engine *e, const char *key, double *value)
 	else if (k == "halo") *value = e->last_H;
 	else if (k == "halo_next") *value = e->opt_halo > 0 ? e->opt_halo : e->cur_halo;
 	else if (k == "nstars") *value = (double)e->stars.size();
+	else if (k == "num_sms") *value = e->num_sms;
+	// nominal FP64 FMA peak at the device's maximum SM clock: SMs x 64 lanes x 2 FLOP x GHz (TFLOP/s)
+	else if (k == "fp64_nominal_tflops") *value = e->num_sms * 64.0 * 2.0 * e->sm_clock_ghz * 1e-3;
 	else if (k == "transit_items") {
 		unsigned int q = 0;
 		const unsigned int *src = e->last_fused ? (e->d_qfused.p ? e->d_qfused.p + 1 : nullptr) : e->d_qcount.p;
@@ -1571,7 +1581,7 @@ int gpt_measure_fp64_peak(gpt_engine *e, double *tflops)
 {
 	if (!e || !tflops) return GPT_E_INVALID;
 	cudaSetDevice(e->device);
-	const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+	const int blocks = e->num_sms * 8, threads = 256, iters = 1 << 14;
 	DevBuf<double> out;
 	CK(out.ensure((size_t)blocks * threads));
 	cudaEvent_t a, b;

@@ -352,7 +352,7 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 		tr.tp = periastron_time(tr.t0, tr.per, tr.ecc, tr.w);
 		transit_window(tr, m.exp_time);
 		double *q = pp + PP_TR;
-		q[0] = tr.per; q[1] = tr.t0; q[2] = tr.rp; q[3] = tr.a; q[4] = tr.inc;
+		q[0] = tr.per; q[1] = tr.t0; q[2] = pars[2]; q[3] = tr.a; q[4] = tr.inc;  // rp keeps its sign (inverse transit)
 		q[5] = tr.ecc; q[6] = tr.w; q[7] = tr.u1; q[8] = tr.u2;
 		pp[PP_TP] = tr.tp;
 		pp[PP_WCEN] = tr.wcen;
@@ -479,7 +479,7 @@ __global__ void prep_wide_kernel(ModelDev m, const StarDev *stars, int W, const 
 		tr.tp = periastron_time(tr.t0, tr.per, tr.ecc, tr.w);
 		transit_window(tr, m.exp_time);
 		double *q = pp + PP_TR;
-		q[0] = tr.per; q[1] = tr.t0; q[2] = tr.rp; q[3] = tr.a; q[4] = tr.inc;
+		q[0] = tr.per; q[1] = tr.t0; q[2] = pars[2]; q[3] = tr.a; q[4] = tr.inc;  // rp keeps its sign (inverse transit)
 		q[5] = tr.ecc; q[6] = tr.w; q[7] = tr.u1; q[8] = tr.u2;
 		pp[PP_TP] = tr.tp;
 		pp[PP_WCEN] = tr.wcen;
@@ -497,7 +497,8 @@ __global__ void prep_wide_kernel(ModelDev m, const StarDev *stars, int W, const 
 __device__ inline void load_transit(const double *pp, TransitPars &tr)
 {
 	const double *q = pp + PP_TR;
-	tr.per = q[0]; tr.t0 = q[1]; tr.rp = q[2]; tr.a = q[3]; tr.inc = q[4];
+	tr.per = q[0]; tr.t0 = q[1]; tr.rp = fabs(q[2]); tr.a = q[3]; tr.inc = q[4];
+	tr.inverse = q[2] < 0.0;
 	tr.ecc = q[5]; tr.w = q[6]; tr.u1 = q[7]; tr.u2 = q[8];
 	tr.tp = pp[PP_TP];
 	tr.wcen = pp[PP_WCEN];
@@ -529,7 +530,7 @@ __global__ void prep_transit_direct_kernel(double exp_time, const double *pars9,
 	tr.tp = periastron_time(tr.t0, tr.per, tr.ecc, tr.w);
 	transit_window(tr, exp_time);
 	double *q = pp + PP_TR;
-	q[0] = tr.per; q[1] = tr.t0; q[2] = tr.rp; q[3] = tr.a; q[4] = tr.inc;
+	q[0] = tr.per; q[1] = tr.t0; q[2] = pars[2]; q[3] = tr.a; q[4] = tr.inc;  // rp keeps its sign (inverse transit)
 	q[5] = tr.ecc; q[6] = tr.w; q[7] = tr.u1; q[8] = tr.u2;
 	pp[PP_TP] = tr.tp;
 	pp[PP_WCEN] = tr.wcen;
@@ -704,6 +705,7 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 				__syncthreads();
 			}
 			const int total = s_off[nthr];
+			__syncthreads();  // every thread has read the total before the next round's scan overwrites s_off
 			for (int f0 = 0; f0 < total; f0 += items_cap) {
 				const int f1 = min(total, f0 + items_cap);
 				if (tid == 0) s_n = 0;
@@ -867,6 +869,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 			const bool on = lane_used && item < nitems;
 			double f = 0.0;
 			int gw = 0, n = 0, N = 0;
+			bool inverse = false;
 			if (on) {
 				const unsigned long long q = queue[item];
 				gw = (int)(q >> 32);
@@ -875,6 +878,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				N = st.N;
 				TransitPars tr;
 				load_transit(prep + (size_t)gw * PREP_STRIDE, tr);
+				inverse = tr.inverse;
 				// np.linspace offsets: start + i*step is numpy's arange(num)*step + start
 				const double ss_start = -exp_time / 2., ss_step = ss > 1 ? exp_time / (ss - 1) : 0.0;
 				const double ts = ss > 1 ? supersample_offset(i, ss, ss_start, ss_step) + st.tdays[n] : st.tdays[n];
@@ -889,6 +893,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 			}
 			if (on && i == 0) {
 				double m = ss > 1 ? s / ss : s;
+				if (inverse) m = 2.0 - m;  // batman: rp < 0 is an inverse transit, light curve 2 - lc
 				out[(size_t)gw * N + n] = dense ? m : (m - 1) * 1e6;  // transit.py:127
 			}
 		}
@@ -905,6 +910,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				s += ma_flux(rsky_one(supersample_offset(i, ss, -exp_time / 2., exp_time / (ss - 1)) + st.tdays[n], tr), tr.rp,
 					     tr.u1, tr.u2, mode);
 			double m = s / ss;
+			if (tr.inverse) m = 2.0 - m;
 			out[(size_t)gw * st.N + n] = dense ? m : (m - 1) * 1e6;
 		}
 	}
@@ -2295,7 +2301,7 @@ __global__ void sampler_rhat_kernel(SamplerDev S, long long first, long long cou
 	extern __shared__ double s_red[];
 	const int star = blockIdx.x / S.ndim, d = blockIdx.x - star * S.ndim;
 	const int W = S.W;
-	double *s_mean = s_red, *s_ss = s_red + blockDim.x;
+	double *s_mean = s_red, *s_ss = s_red + (W > (int)blockDim.x ? W : (int)blockDim.x);  // matches the host's allocation
 	double gm = 0.0;
 	// pass 1: per-walker means
 	for (int w = threadIdx.x; w < W; w += blockDim.x) {

@@ -147,8 +147,7 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
  *   naccept [nstars][W] (optional)
  * step0 is the number of iterations already done (resume, model.py:235-253):
  * the Philox stream is keyed by (seed, star id, step0 + i, walker) so results
- * do not depend on how the run is split or on the number of GPUs.
- * thin >= 1 keeps every thin-th step (nsteps must be a multiple). */
+ * do not depend on how the run is split or on the number of GPUs.  Every step is kept. */
 int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, int64_t nsteps,
 	       uint64_t seed, uint64_t step0, double a, double *chain, double *logp, int64_t *naccept);
 

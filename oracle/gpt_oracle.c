@@ -636,6 +636,9 @@ void orc_light_curve(const double *t, int N, const double *pars9, int ss, double
 		} else {
 			out_flux[n] = fl[n];
 		}
+		/* batman (>= 2.4.6, transitmodel.py light_curve) [recalled]: rp < 0 is an "inverse transit":
+		 * the model is computed for |rp| and returned as 2 - lc */
+		if (rp < 0.0) out_flux[n] = 2.0 - out_flux[n];
 	}
 	free(tss);
 	free(ds);
