@@ -92,8 +92,6 @@ struct gpt_engine {
 	long long spec_need_steps = 128;  // clean record needed before a block runs speculatively; doubles on a replay
 	bool spec_last_clean = true;
 	long long n_spec_replays = 0;
-	int opt_ctas_per_sm = 1;
-	double opt_min_chunk_halos = 1.0;   // chunk length >= this many halos
 	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
 	int cur_halo = 0;         // 0: derive from the priors at the first evaluation
 	double prior_cmin = 0.0;  // smallest celerite decay rate c the priors allow (rad per megasecond)
@@ -107,6 +105,7 @@ struct gpt_engine {
 	DevBuf<double> d_theta, d_lp, d_parts, d_prep, d_mean, d_carryT, d_carryE;
 	DevBuf<int> d_flags, d_wstatus, d_wbad;
 	DevBuf<ChunkPartial> d_partial;
+	DevBuf<ChunkPartial> d_partial2;  // [nwalk] results of the sequential recomputation of flagged walkers
 	DevBuf<unsigned char> d_redo;
 	DevBuf<unsigned long long> d_queue;  // transit work queue: (walker << 32) | sample
 	DevBuf<unsigned int> d_qcount;
@@ -256,8 +255,7 @@ static int check_stars(gpt_engine *e, int star0, int nstars)
 	return GPT_OK;
 }
 
-// chunk geometry: "ctas_per_sm" warps per SM sub-partition worth of (walker, chunk) threads, but never
-// chunks shorter than "min_chunk_halos" halos (each chunk recomputes one halo)
+// chunk geometry: halo from the priors / the adaptation, number of chunks from the measured cost model
 static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, int &nchunks, int &L, int &H)
 {
 	if (e->opt_halo > 0) {
@@ -515,12 +513,13 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	CK(e->d_carryE.ensure((size_t)nwalk * nchunks * CS));
 	CK(e->d_partial.ensure((size_t)nwalk * nchunks));
 	CK(e->d_redo.ensure((size_t)nwalk * nchunks));
+	CK(e->d_partial2.ensure((size_t)nwalk));
 	CK(e->d_wbad.ensure(nwalk));
 
 	ChunkArgs a;
 	a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
 	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
-	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p;
+	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p; a.wbad = e->d_wbad.p; a.partial2 = e->d_partial2.p;
 	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
 	a.min_order = e->opt_series_order_min;
 	const int cthreads = chunk_threads(W);
@@ -539,6 +538,8 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	f.skip_if_clean = 0;
 	f.acc = e->d_acc.p;
 	f.wbad = e->d_wbad.p;
+	f.partial2 = e->d_partial2.p;
+	f.L = L;
 	f.tol = e->opt_tol;
 	f.qreset = fuse_scan ? e->d_qfused.p : nullptr;
 	memset(&f.AC, 0, sizeof(f.AC));
@@ -578,8 +579,11 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 			e->adapt_halo(H, need, e->last_verr);
 		}
 		if (need) {
-			// pass 2 exits at once on the device when nothing was flagged, so the asynchronous
-			// path can enqueue it unconditionally (no host round trip inside a sampler step)
+			// Pass 2 exits at once on the device when nothing was flagged, so the asynchronous path can enqueue
+			// it unconditionally (no host round trip inside a sampler step).  A flagged chunk is redone exactly
+			// from the carry its predecessor left in pass 1; walkers for which that carry cannot be trusted
+			// (the predecessor flagged as well, by more than a chunk's worth of decay makes up for) are recomputed whole,
+			// sequentially, by the CTAs of chunk 0 of the same launch (gp_finalize_kernel decides).
 			a.pass2 = 1;
 			e->timer_begin(TK_PASS2);
 			launch_chunk(nt, m.has_transit != 0, grid, cthreads, st, a);
@@ -650,7 +654,7 @@ void gpt_engine_destroy(gpt_engine *e)
 	e->d_stars.release();
 	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
 	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
-	e->d_partial.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
+	e->d_partial.release(); e->d_partial2.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
 	e->d_queue.release(); e->d_qcount.release(); e->d_qfused.release(); e->d_wbad.release();
 	e->s_x.release(); e->s_lpx.release(); e->s_q.release(); e->s_lq.release(); e->s_fac.release();
 	e->s_chain.release(); e->s_logp.release(); e->s_act.release(); e->s_ids.release(); e->s_nacc.release();
@@ -674,10 +678,6 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 		e->opt_chunks = (int)value;
 	} else if (k == "verify") {
 		e->opt_verify = value != 0;
-	} else if (k == "ctas_per_sm") {
-		e->opt_ctas_per_sm = std::max(1, (int)value);
-	} else if (k == "min_chunk_halos") {
-		e->opt_min_chunk_halos = value;
 	} else if (k == "transit_strict") {
 		e->opt_transit_strict = value != 0;
 	} else if (k == "series_order_min") {

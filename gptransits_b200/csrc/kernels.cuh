@@ -927,6 +927,8 @@ struct ChunkArgs {
 	ChunkPartial *partial;    // [nwalk][nchunks]
 	int *wstatus;             // [nwalk] OR of WF_NOTPD
 	const unsigned char *redo;  // [nwalk][nchunks] (pass 2)
+	const int *wbad;            // [nwalk] (pass 2) 1: redo the flagged chunks from the carries of pass 1, 2: recompute the whole walker
+	ChunkPartial *partial2;     // [nwalk] results of whole-walker recomputations
 	const int *nbad;          // [1] pass 2 exits at once when zero
 	int W;                    // walkers per star
 	int N, nchunks, L, H;
@@ -1220,7 +1222,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	const StarDev st = A.stars[star];
 	const int N = A.N;
 	const int n0 = c * A.L;
-	const int n1 = min(N, n0 + A.L);
+	int n1 = min(N, n0 + A.L);
 	const bool pass2 = A.pass2 != 0;
 	if (pass2 || !TRANSIT) {
 		// pass 2: the verdict comes from the finalize kernel right before this launch; without a transit
@@ -1236,10 +1238,15 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	if (w < A.W) {
 		fl = A.flags[gw];
 		active = (fl & WF_VALID) && !(fl & WF_GENERIC);
-		if (pass2 && active) active = A.redo[(size_t)gw * A.nchunks + c] != 0;
+		// pass 2: chunks c > 0 redo their flagged (walker, chunk) pairs from the carry of pass 1; chunk 0 -- never
+		// flagged itself -- takes the walkers that are recomputed whole, sequentially from the first sample
+		if (pass2 && active)
+			active = c == 0 ? A.wbad[gw] == 2 : (A.wbad[gw] == 1 && A.redo[(size_t)gw * A.nchunks + c] != 0);
 	}
 	if (n0 >= N) return;
 	if (!__syncthreads_or(active)) return;
+	const bool whole = pass2 && c == 0;  // block-uniform: this CTA walks the whole light curve
+	if (whole) n1 = N;
 
 	// ---- walker coefficients -> registers
 	const double *pp = A.prep + (size_t)(active ? gw : 0) * PREP_STRIDE;
@@ -1576,7 +1583,8 @@ GP_PRAGMA_UNROLL
 	}
 
 	if (active) {
-		if (c + 1 < A.nchunks && n1 < N) store_carry(A.carryT + ((size_t)gw * A.nchunks + c + 1) * CS);
+		// (pass 2 leaves the carries alone: a neighbouring chunk that is being redone reads them at the same time)
+		if (!pass2 && c + 1 < A.nchunks && n1 < N) store_carry(A.carryT + ((size_t)gw * A.nchunks + c + 1) * CS);
 		ChunkPartial pr;
 		pr.quad = S.quad;
 		pr.logdet = (double)S.lde * 0.693147180559945309417 + log(S.ldm);
@@ -1586,7 +1594,8 @@ GP_PRAGMA_UNROLL
 			pr.logdet = CUDART_NAN;
 			atomicOr(&A.wstatus[gw], WF_NOTPD);
 		}
-		A.partial[(size_t)gw * A.nchunks + c] = pr;
+		if (whole) A.partial2[gw] = pr;
+		else A.partial[(size_t)gw * A.nchunks + c] = pr;
 	}
 }
 
@@ -1606,7 +1615,10 @@ struct FinalArgs {
 	int verify;     // 1: compare carries and flag chunks; 0: just reduce
 	int skip_if_clean;  // second invocation: nothing to do when pass 1 flagged no chunk
 	unsigned long long *acc;  // [2] running totals over calls: flagged chunks, max error ratio (bits)
-	int *wbad;      // [nwalk] 1: the walker had a flagged chunk (its result is final only after pass 2)
+	int *wbad;      // [nwalk] the walker had a flagged chunk (its result is final only after pass 2): 1 = its flagged chunks are
+	                // redone from the carries of pass 1, 2 = it is recomputed whole (see below)
+	const ChunkPartial *partial2;  // [nwalk] second invocation: results of the whole-walker recomputations
+	int L;          // chunk length
 	double tol;
 	unsigned int *qreset;  // fused-scan item counter: [1] = [0], [0] = 0 for the next evaluation (or null)
 	FinalAccept AC;
@@ -1731,10 +1743,17 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 		return;
 	}
 	double q = 0.0, ld = 0.0;
-	for (int k = tid; k < A.nchunks; k += FIN_THREADS) {
-		ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
-		q += pr.quad;
-		ld += pr.logdet;
+	if (A.skip_if_clean && A.wbad[gw] == 2) {
+		if (tid == 0) {
+			q = A.partial2[gw].quad;
+			ld = A.partial2[gw].logdet;
+		}
+	} else {
+		for (int k = tid; k < A.nchunks; k += FIN_THREADS) {
+			ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
+			q += pr.quad;
+			ld += pr.logdet;
+		}
 	}
 	// carries of this thread's first boundary, requested before the sums synchronise the block
 	const bool do_verify = A.verify && A.nchunks > 1;
@@ -1803,7 +1822,12 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			double r = fmax(errL / budL, errQ / budQ);
 			bool bad = !(r <= 1.0);  // NaN -> redo
 			if (isfinite(r)) worst = fmax(worst, r);
-			A.redo[(size_t)gw * A.nchunks + k] = bad ? 1 : 0;
+			// The carry a flagged chunk leaves at its END has decayed over the chunk as the estimate did over the
+			// halo: by (error / state)^(L / H) more.  Bit 1: even so it would not pass (with a margin of 10) as
+			// the start of the next chunk's repair.
+			const double decay = exp(log(fmin(fmax(fmax(eS / fmax(nS, 1e-300), ef / fmax(nf, 1e-300)), 1e-300), 1.0)) * ((double)A.L / Hh));
+			const bool end_bad = bad && !(r * decay <= 0.1);
+			A.redo[(size_t)gw * A.nchunks + k] = bad ? (end_bad ? 3 : 1) : 0;
 			nbad += bad ? 1 : 0;
 		}
 		if (tid == 0) A.redo[(size_t)gw * A.nchunks] = 0;
@@ -1820,7 +1844,17 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
 			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
-		walker_bad = __syncthreads_or(nbad > 0);
+		walker_bad = __syncthreads_or(nbad > 0) ? 1 : 0;
+		if (walker_bad) {
+			// A flagged chunk is redone exactly from the carry its predecessor left in pass 1.  That carry is as good
+			// as the predecessor's own start after one more chunk of decay: fine when the predecessor passed, and
+			// when it was flagged by a margin the chunk's length makes up for (redo bit 1 clear).  Otherwise
+			// nothing vouches for it and the walker is recomputed whole.
+			int consec = 0;
+			for (int k = k0; k < A.nchunks; k += FIN_THREADS)
+				if (k > 1 && A.redo[(size_t)gw * A.nchunks + k] && (A.redo[(size_t)gw * A.nchunks + k - 1] & 2)) consec = 1;
+			if (__syncthreads_or(consec)) walker_bad = 2;
+		}
 	}
 	if (tid == 0) {
 		if (!A.skip_if_clean && A.wbad) A.wbad[gw] = walker_bad;

@@ -84,7 +84,7 @@ const char *gpt_last_error(const gpt_engine *e);
 const char *gpt_version(void);
 
 /* Tunables: "halo" (fixed halo length, 0 = adaptive), "chunks" (0 = cost model), "verify", "verify_tol",
- * "halo_auto", "adapt_every" (sampler steps per block), "ctas_per_sm", "min_chunk_halos", "epoch_scan",
+ * "halo_auto", "adapt_every" (sampler steps per block), "epoch_scan",
  * "fuse_scan" (epoch scan inside the prep kernel for small batches, default 1), "transit_strict" (batman's
  * operation order), "series_order_min" (0..4: lowest treatment of regular-cadence steps, 4 = general loop),
  * "pdl" (programmatic dependent launch, default 0), "speculate" (sampler blocks without repair launches,

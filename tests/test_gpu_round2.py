@@ -1,0 +1,150 @@
+"""GPU parity, round 2: the headline (bench) geometry, batman's inverse transit, wide ensembles."""
+import numpy as np
+import pytest
+
+import oracle
+from gptransits_b200 import BatmanModel, GPModel, build_spec, synth
+from test_gpu_parity import C3_CONFIG_GP, C3_CONFIG_TR, assert_parts_close, rel, synthetic_star
+
+pytestmark = pytest.mark.gpu
+
+
+def c3_model(t, with_transit=True, seed=7, W=32):
+    cfg = synth.c3_config()
+    np.random.seed(seed)
+    gp = GPModel(cfg["gp"])
+    tr = None
+    if with_transit:
+        tr = BatmanModel(cfg["transit"][0])
+        tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(gp, tr)
+    blocks = [gp.sample_prior(W)] + ([tr.sample_prior(W)] if tr is not None else [])
+    return spec, np.hstack(blocks)
+
+
+def test_c3_half_ensemble_at_the_bench_geometry(engine):
+    """The headline shape: N = 65 536, 128 walkers per launch (a half-ensemble of 256), automatic geometry
+    and adapted halo; 16 of the walkers against the oracle, quad and log-det separately."""
+    t, y, yerr = synth.make_star(65536, seed=2452144)
+    y = 1e6 + y
+    spec, theta = c3_model(t, True, seed=42, W=128)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    for _ in range(3):                                 # let the halo adapt as it does in the sampler
+        lp, parts = engine.log_prob(theta, return_parts=True)
+    assert engine.stat("chunks") >= 32
+    idx = np.arange(0, 128, 8)
+    _, want = oracle.log_prob(spec, t, y, yerr, theta[idx], return_parts=True, nthreads=8)
+    assert_parts_close(parts[idx], want)
+    # and the whole 256-walker ensemble through the sampler: stored log-probabilities are those of the
+    # stored positions
+    spec, init = c3_model(t, True, seed=43, W=256)
+    chain, logp, _ = engine.sample(init, 3, seed=5)
+    sub = np.arange(0, 256, 32)
+    want_lp = oracle.log_prob(spec, t, y, yerr, chain[sub, -1, :], nthreads=8)
+    assert rel(logp[-1, sub], want_lp) < 1e-9
+
+
+def test_inverse_transit_for_negative_radius_ratio(engine, sim_lc):
+    """batman returns 2 - lc for rp < 0 (an "inverse transit"); a normal prior on Rrat reaches it."""
+    t = sim_lc[0]
+    pars = np.array([[5.778, 3.233, 0.05, 13.83, 88.9, 0.0, 90.0, 0.4996, 0.0847],
+                     [5.778, 3.233, -0.05, 13.83, 88.9, 0.0, 90.0, 0.4996, 0.0847]])
+    spec = build_spec(GPModel(C3_CONFIG_GP), None)
+    tr = BatmanModel(C3_CONFIG_TR)
+    tr.init_model(t, t[1] - t[0], 6)
+    spec = build_spec(GPModel(C3_CONFIG_GP), tr)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, np.zeros(t.size), None)
+    flux = engine.transit_flux(pars)
+    for k in range(2):
+        want = oracle.light_curve(t, pars[k], 6, spec["exp_time"])
+        assert np.max(np.abs(flux[k] - want)) < 1e-9
+    assert np.max(np.abs(flux[1] - (2.0 - flux[0]))) < 1e-15 and flux[1].max() > 1.001
+    # through the posterior: Rrat ~ normal(0, 0.05)
+    cfg = {"params": {"values": dict(C3_CONFIG_TR["params"]["values"], Rrat=[False, None, "normal", 0.0, 0.05])}}
+    tr2 = BatmanModel(cfg)
+    tr2.init_model(t, t[1] - t[0], 6)
+    gp = GPModel(C3_CONFIG_GP)
+    spec2 = build_spec(gp, tr2)
+    np.random.seed(31)
+    theta = np.hstack([gp.sample_prior(48), tr2.sample_prior(48)])
+    assert (theta[:, gp.ndim + 2] < 0).sum() >= 10
+    rng = np.random.default_rng(3)
+    y = 1e6 + rng.normal(0, 150, t.size)
+    engine.set_model(spec2)
+    engine.upload_star(0, t, y, None)
+    _, parts = engine.log_prob(theta, return_parts=True)
+    _, want = oracle.log_prob(spec2, t, y, None, theta, return_parts=True, nthreads=8)
+    assert_parts_close(parts, want)
+
+
+def test_device_gelman_rubin_with_512_walkers(engine):
+    """More walkers than the diagnostic kernel's block size (its shared-memory rows must not alias)."""
+    from gptransits_b200 import convergence
+    rng = np.random.default_rng(1)
+    N = 300
+    t = np.arange(N) * 0.02
+    y = rng.normal(0, 50.0, N)
+    wn = [{"type": "white_noise", "params": {"values": {"jitter": [False, None, "uniform", 1, 300]}}}]
+    gp = GPModel(wn)
+    spec = build_spec(gp, None)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, np.full(N, 1e-3))
+    np.random.seed(2)
+    init = gp.sample_prior(512)
+    engine.sampler_begin(init, seed=5)
+    engine.sampler_run(40, keep=True)
+    chain, _ = engine.sampler_read(0, 40)
+    rhat = engine.sampler_rhat(10, 30)
+    engine.sampler_end()
+    want, _, _ = convergence.gelman_rubin(chain[0][:, 10:40, :])
+    assert rel(rhat[0], want) < 1e-10
+
+def test_flagged_chunks_are_repaired_whatever_the_geometry(engine):
+    """A flagged chunk is redone from the carry its predecessor left, unless the predecessor was flagged too: then
+    nothing vouches for that carry and the walker is recomputed whole.  A useless halo gets chunks flagged all
+    over, with chunks shorter and longer than the halo; the results must still be the oracle's, through the
+    posterior call and through the sampler (asynchronous repair)."""
+    t, y, yerr = synthetic_star(4096, 6)
+    np.random.seed(9)
+    gp = GPModel(C3_CONFIG_GP)
+    spec = build_spec(gp, None)
+    theta = gp.sample_prior(16)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, y, yerr)
+    _, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+    try:
+        engine.set_option("chunks", 64)
+        engine.set_option("halo", 400)                 # chunks of 64 samples behind a halo of 400
+        _, parts = engine.log_prob(theta, return_parts=True)
+        assert engine.stat("chunks") == 64
+        assert_parts_close(parts, want)
+        engine.set_option("halo", 8)                   # far too short: chunks flagged all over
+        before = engine.stat("pass2_chunks")
+        _, parts = engine.log_prob(theta, return_parts=True)
+        assert engine.stat("pass2_chunks") > before + 16
+        assert_parts_close(parts, want)
+        # chunks longer than the (useless) halo: the chunk-by-chunk repair
+        engine.set_option("chunks", 8)
+        engine.set_option("halo", 2)
+        before = engine.stat("pass2_chunks")
+        _, parts = engine.log_prob(theta, return_parts=True)
+        assert engine.stat("pass2_chunks") > before
+        assert_parts_close(parts, want)
+        # the same through the sampler (asynchronous repair launches), both repair forms
+        ochain, ologp, onacc = oracle.sample(spec, t, y, yerr, theta, 4, seed=13)
+        engine.set_option("speculate", 0)
+        for chunks, halo in ((64, 8), (8, 2)):
+            engine.set_option("chunks", chunks)
+            engine.set_option("halo", halo)
+            chain, logp, nacc = engine.sample(theta, 4, seed=13)
+            assert np.array_equal(nacc, onacc) and rel(chain, ochain) < 1e-9
+    finally:
+        engine.set_option("speculate", 1)
+        engine.set_option("chunks", 0)
+        engine.set_option("halo", 0)

@@ -30,7 +30,6 @@ def main():
         for halo in (320,):
             eng.set_option("chunks", chunks)
             eng.set_option("halo", halo)
-            eng.set_option("min_chunk_halos", 0.25)
             eng.log_prob(theta)
             eng.log_prob(theta)
             p2 = eng.stat("pass2_chunks")
