@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="engine option (gpt_set_option), e.g. --opt pdl=0; recorded in config")
+    ap.add_argument("--no-splits", action="store_true", help="skip the c4_strong / walker_sharded sub-records")
     ap.add_argument("--batch-walkers", type=int, default=2048,
                     help="size of the extra resident log_prob batch (0 = skip)")
     return ap.parse_args()
@@ -206,8 +207,11 @@ def run_reference(args):
         y = 1e6 + work["ys"][0] + (flux - 1) * 1e6
     cores = os.cpu_count() or 1
     W = work["W"]
-    nsample = args.cpu_evals or min(W, max(2 * cores, 32))
-    theta = draw_prior(gp, tr, nsample)
+    # one step = the evaluations one ensemble step of our arm makes on one GPU (W per star); the stars of a batch
+    # share the model, so star 0 stands for all of them
+    nsample = args.cpu_evals or W * len(work["ys"])
+    theta = draw_prior(gp, tr, min(nsample, 4096))
+    theta = theta[np.resize(np.arange(theta.shape[0]), nsample)]
     for _ in range(args.warmup):
         cpu_evals_per_s(spec, t, y, work["yerr"], theta[:cores], cores)
     times = []
@@ -216,7 +220,8 @@ def run_reference(args):
         times.append(dt)
     total = float(np.sum(times))
     value = nsample * args.steps / total
-    sample = f"{nsample} posterior evaluations per step of the {args.workload} workload, {cores} OpenMP threads"
+    sample = (f"{nsample} posterior evaluations per step (one ensemble step of the {args.workload} workload on one GPU; "
+              f"star 0 stands for every star), {cores} OpenMP threads, oracle port of celerite+batman arithmetic")
     out = {"impl": "reference", "metric": "log-likelihood evals/s (walkers x steps)", "value": value,
            "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -240,6 +245,113 @@ def hbm_view(algorithmic_bytes, kernel_ms):
         return None
     gbs = algorithmic_bytes / (kernel_ms * 1e-3) / 1e9
     return {"achieved_gbs": gbs, "peak_gbs": peak, "peak_source": src, "frac": gbs / peak}
+
+
+# --------------------------------------------------------------------------- parity at the bench geometry
+def parity_check(eng, spec, t, ys, yerr, x, lpx, W, nstars, per_star=16, max_stars=8):
+    """The final ensemble of the timed run against the CPU oracle, outside the timed region: the first half of
+    every star's walkers is evaluated in one launch of the sampler's own shape (W/2 walkers per star, all stars:
+    the same chunk geometry and halo) and `per_star` of them on up to `max_stars` stars are compared term by
+    term; the log-probabilities the sampler itself stored for those walkers are compared too."""
+    import oracle
+    H = W // 2
+    ndim = x.shape[-1]
+    th = np.ascontiguousarray(x[:, :H, :])
+    _, parts = eng.log_prob(th, nstars=nstars, return_parts=True)
+    geom = {k: eng.stat(k) for k in ("chunks", "chunk_len", "halo")}
+    stars = np.unique(np.linspace(0, nstars - 1, min(nstars, max_stars)).astype(int))
+    sel = np.unique(np.linspace(0, H - 1, min(H, per_star)).astype(int))
+    worst = {"quad": 0.0, "logdet": 0.0, "lnprior": 0.0, "lp_sampler": 0.0}
+    n = 0
+    for s in stars:
+        want_lp, want = oracle.log_prob(spec, t, ys[s], yerr, th[s, sel], return_parts=True, nthreads=os.cpu_count() or 1)
+        got = parts[s, sel]
+        fin = np.isfinite(want[:, 3])
+        if not np.array_equal(np.isfinite(got[:, 3]), fin):
+            worst["quad"] = float("inf")
+        for name, col in (("lnprior", 0), ("quad", 1), ("logdet", 2)):
+            if fin.any():
+                d = np.abs(got[fin, col] - want[fin, col]) / np.maximum(np.abs(want[fin, col]), 1e-300)
+                worst[name] = max(worst[name], float(d.max()))
+        f2 = np.isfinite(want_lp)
+        if f2.any():
+            d = np.abs(lpx[s, sel][f2] - want_lp[f2]) / np.maximum(np.abs(want_lp[f2]), 1e-300)
+            worst["lp_sampler"] = max(worst["lp_sampler"], float(d.max()))
+        n += int(sel.size)
+    ok = all(v < 1e-9 for v in worst.values())
+    return {"n": n, "stars": int(stars.size), "max_rel_quad": worst["quad"], "max_rel_logdet": worst["logdet"],
+            "max_rel_lnprior": worst["lnprior"], "max_rel_lp_sampler": worst["lp_sampler"], "tolerance": 1e-9,
+            "chunks": geom["chunks"], "chunk_len": geom["chunk_len"], "halo": geom["halo"], "ok": bool(ok)}
+
+
+def chain_hash(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.round(a, 6)).tobytes()).hexdigest()[:16]
+
+
+def north_star_splits(eng, args, rank, world, dist, barrier, max_over_ranks):
+    """The two multi-GPU splits BASELINE.json names, measured in the same run at every N (N = 1 included, so the
+    scaling of each is value_N / value_1):
+      c4_strong       1024 stars x 64 walkers x N = 4096 sharded by star, no collective: evals/s of the whole job
+      walker_sharded  ONE C3 star, 256 walkers, the active half-ensemble sharded by walker; the proposal
+                      log-probabilities are all-gathered over NVLink (NCCL on the engine's stream): ms per step,
+                      and a hash of the chain that must not depend on N"""
+    from gptransits_b200 import synth
+    from gptransits_b200.parallel import run_walker_sharded
+    out = {}
+    steps, warm = 5, 3
+    # ---- C4 strong
+    class A4:
+        walkers = 0
+        gpus = world
+    work = build_workload("c4", rank, A4)
+    t = work["t"]
+    np.random.seed(args.seed)
+    gp, tr, spec = model_of(work, t)
+    eng.clear_stars()
+    ys = inject_transit(eng, work, spec)
+    for s_, y in enumerate(ys):
+        eng.upload_star(s_, t, y, work["yerr"])
+    ns, W = len(ys), work["W"]
+    ndim = spec["prior_kind"].size
+    np.random.seed(args.seed + 17 + rank)
+    init = draw_prior(gp, tr, W * ns).reshape(ns, W, ndim)
+    eng.sampler_begin(init, seed=args.seed, nstars=ns, star_ids=work["star_ids"])
+    eng.sampler_run(warm, keep=False)
+    barrier()
+    ms = eng.sampler_run_timed(steps, keep=False, flush_l2=True)
+    eng.sampler_end()
+    tot = max_over_ranks(float(ms.sum()))
+    out["c4_strong"] = {"value": 1024 * W * steps / (tot * 1e-3), "unit": "evals/s", "ms_per_step": tot / steps,
+                        "stars_per_gpu": ns, "steps": steps, "scaling": "strong", "collective": None}
+    # ---- one C3 star, walkers sharded
+    class A3:
+        walkers = 0
+        gpus = 1
+    work = build_workload("c3", 0, A3)     # the same star on every rank
+    t = work["t"]
+    np.random.seed(args.seed)
+    gp, tr, spec = model_of(work, t)
+    eng.clear_stars()
+    ys = inject_transit(eng, work, spec)
+    eng.upload_star(0, t, ys[0], work["yerr"])
+    W = work["W"]
+    np.random.seed(args.seed + 5)
+    init = draw_prior(gp, tr, W)
+    run_walker_sharded(eng, dist, init, warm, seed=args.seed)          # warm-up (halo, communicator)
+    barrier()
+    chain, logp, ms = run_walker_sharded(eng, dist, init, steps, seed=args.seed, timed=True)
+    tot = max_over_ranks(float(ms.sum()))
+    h = chain_hash(chain)
+    same = True
+    if dist is not None:
+        hs = [None] * world
+        dist.all_gather_object(hs, h)
+        same = len(set(hs)) == 1
+    out["walker_sharded"] = {"ms_per_step": tot / steps, "value": W * steps / (tot * 1e-3), "unit": "evals/s",
+                             "walkers": W, "steps": steps, "chain_hash": h, "hash_equal_across_ranks": bool(same),
+                             "collective": "ncclAllGather of W/2 doubles, twice per step, on the engine's stream"}
+    return out
 
 
 # --------------------------------------------------------------------------- our arm
@@ -285,6 +397,7 @@ def run_ours(args):
     star_ids = work.get("star_ids")
     flush = not args.no_flush
     peak_tf = eng.fp64_peak_tflops()
+    peak_nom = eng.stat("fp64_nominal_tflops")   # SMs x 64 lanes x 2 FLOP x max SM clock
 
     def barrier():
         if dist is not None:
@@ -320,7 +433,7 @@ def run_ours(args):
     kern = {k: (eng.stat("ms_" + k), eng.stat("n_" + k)) for k in ("prep", "transit", "trscan", "chunk", "final", "pass2")}
     eng.set_option("time_kernels", 0)
     clk = clocks.stop()
-    _, _, nacc = eng.sampler_state()
+    xfin, lpfin, nacc = eng.sampler_state()
     eng.sampler_end()
     chunk_ms, chunk_n = kern["chunk"]
     walkers_per_launch = (W // 2) * nstars
@@ -380,6 +493,17 @@ def run_ours(args):
                    "whole_eval_frac": (F_GP[J] + f_tr) * N * WB / (float(np.median(msb)) * 1e-3) / 1e12 / peak_tf,
                    "chunks": eng.stat("chunks"), "chunk_len": eng.stat("chunk_len"), "halo": eng.stat("halo")}
 
+    # ---- parity of the final ensemble at the bench geometry (outside every timed region)
+    parity = None
+    if rank == 0:
+        import oracle
+        oracle.build()
+        parity = parity_check(eng, spec, t, ys, work["yerr"], xfin, lpfin, W, nstars)
+
+    splits = None
+    if not args.no_splits and args.workload == "c3":
+        splits = north_star_splits(eng, args, rank, world, dist, barrier, max_over_ranks)
+
     cpu = None
     if rank == 0 and world == 1:
         import oracle
@@ -418,8 +542,7 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
                          "peak_source": "measured on this GPU by gpt_measure_fp64_peak (DFMA kernel); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
-                         "frac_counting_halo_steps": ((achieved_tf / peak_tf) * (1.0 + (stats["halo"] / stats["chunk_len"]
-                                                      if stats["chunks"] > 1 else 0.0))) if achieved_tf else None,
+                         "peak_nominal": peak_nom, "frac_of_nominal": (achieved_tf / peak_nom) if achieved_tf and peak_nom else None,
                          "flops_per_launch": flops_per_launch, "kernel_ms": chunk_ms / max(chunk_n, 1),
                          "kernel_launches_timed": chunk_n, "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
                          "hbm_algorithmic_bytes_per_launch": bytes_per_launch, "traffic": traffic,
@@ -429,6 +552,9 @@ def run_ours(args):
                          "pass2_chunks": stats["pass2_chunks"], "verify_ratio": stats["verify_ratio"]},
             "clocks": clk,
         }
+        out["parity_check"] = parity
+        if splits:
+            out["north_star_splits"] = splits
         if batched:
             out["batched_log_prob"] = batched
         if cpu:
@@ -437,6 +563,8 @@ def run_ours(args):
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        sys.exit("parity check against the oracle failed: " + json.dumps(parity))
 
 
 if __name__ == "__main__":

@@ -104,6 +104,10 @@ SIGNATURES = {
     "gpt_sampler_lq_device": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "gpt_sampler_half_eval": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "gpt_sampler_half_accept": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gpt_comm_id": (C.c_int, [_vp]),
+    "gpt_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "gpt_comm_destroy": (C.c_int, [_vp]),
+    "gpt_sampler_run_sharded": (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "gpt_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "gpt_sampler_run_timed": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "gpt_log_prob_device_timed": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,

@@ -5,6 +5,9 @@
 #include "../../include/gptransits_b200.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is opened at run time (gpt_comm_*), never linked
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -118,6 +121,10 @@ struct gpt_engine {
 	size_t h_stage_cap = 0;
 	int *h_nbad = nullptr;   // pinned
 	double *h_verr = nullptr;
+
+	// NCCL communicator of the walker-sharded sampler (gpt_comm_init)
+	ncclComm_t comm = nullptr;
+	int comm_rank = 0, comm_world = 1;
 
 	// sampler
 	bool sampling = false;
@@ -275,8 +282,8 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 		nc = e->opt_chunks;
 	} else {
 		// Cost model (measured on B200): every thread runs N/nc + H dependent steps; up to one warp
-		// per SM sub-partition they all run concurrently at the single-warp step time, two resident
-		// warps share the FP64 pipe at 1.21x the single-warp throughput, more warps queue up.
+		// per SM sub-partition they all run concurrently at the single-warp step time, more resident
+		// warps share the sub-partition's issue slots and FP64 pipe with little gain.
 		const int cthreads = std::min(CHUNK_THREADS, ((W + 31) / 32) * 32);
 		const double wpl = (double)nstars * ((W + cthreads - 1) / cthreads) * (cthreads / 32);  // warps per chunk layer
 		const double slots = (double)e->num_sms * 4.0;
@@ -287,7 +294,9 @@ static void pick_geometry(gpt_engine *e, int star0, int N, int W, int nstars, in
 			const double h = cand == 1 ? 0.0 : (double)H;
 			const double wps = cand * wpl / slots;
 			double slow = 1.0;
-			if (wps > 1.0) slow = wps <= 2.0 ? 1.0 + (wps - 1.0) * (2.0 / 1.21 - 1.0) : wps / 1.21;
+			// (measured on C3 and on the C4 batch at 1/2/4/8 GPUs: a step function -- the kernel lasts as long as the
+			// SM with the most CTAs, and k warps on a sub-partition take 0.885 k times one warp's time per step)
+			if (wps > 1.0) slow = std::ceil(wps - 1e-9) * 0.885;
 			const double cost = ((double)N / cand + h) * slow + 0.05 * cand;
 			if (cost < best * 0.999) {
 				best = cost;
@@ -365,11 +374,23 @@ static void launch_finalize(int nt, int nwalk, cudaStream_t st, const FinalArgs 
 		launch_k(gp_finalize_wide_kernel, dim3((nwalk + FINW_THREADS / 32 - 1) / (FINW_THREADS / 32)), dim3(FINW_THREADS), 0, st, f);
 		return;
 	}
+	// thousands of walkers cut into a few chunks: one warp per walker; otherwise one block per walker
+	if (nwalk >= 1024 && f.nchunks <= 64) {
+		const dim3 g((nwalk + FINW_WALKERS - 1) / FINW_WALKERS), b(32 * FINW_WALKERS);
+		switch (nt) {
+		case 1: launch_k(gp_finalize_kernel<1, 32>, g, b, 0, st, f); break;
+		case 2: launch_k(gp_finalize_kernel<2, 32>, g, b, 0, st, f); break;
+		case 3: launch_k(gp_finalize_kernel<3, 32>, g, b, 0, st, f); break;
+		case 4: launch_k(gp_finalize_kernel<4, 32>, g, b, 0, st, f); break;
+		default: break;
+		}
+		return;
+	}
 	switch (nt) {
-	case 1: launch_k(gp_finalize_kernel<1>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
-	case 2: launch_k(gp_finalize_kernel<2>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
-	case 3: launch_k(gp_finalize_kernel<3>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
-	case 4: launch_k(gp_finalize_kernel<4>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 1: launch_k(gp_finalize_kernel<1, FIN_THREADS>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 2: launch_k(gp_finalize_kernel<2, FIN_THREADS>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 3: launch_k(gp_finalize_kernel<3, FIN_THREADS>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
+	case 4: launch_k(gp_finalize_kernel<4, FIN_THREADS>, dim3(nwalk), dim3(FIN_THREADS), 0, st, f); break;
 	default: break;
 	}
 }
@@ -647,6 +668,7 @@ int gpt_star_clear(gpt_engine *e)
 
 void gpt_engine_destroy(gpt_engine *e)
 {
+	if (e && e->comm) gpt_comm_destroy(e);
 	if (!e) return;
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
@@ -1466,6 +1488,170 @@ int gpt_sampler_half_accept(gpt_engine *e, int half, int keep)
 		e->s_step++;
 	}
 	CK(cudaGetLastError());
+	return GPT_OK;
+}
+
+// ---- walker-sharded sampling of one star across GPUs: the all-gather runs on the engine's stream -------------
+namespace {
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+static NcclApi &nccl_api()
+{
+	static NcclApi api;
+	if (api.handle) return api;
+	// the copy a host framework has already loaded is found first; otherwise the system library
+	for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+		api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+		if (api.handle) break;
+	}
+	if (!api.handle) return api;
+	api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+	api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+	api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+	api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+	api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+	api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+	return api;
+}
+}  // namespace
+
+int gpt_comm_id(void *id128)
+{
+	if (!id128) return GPT_E_INVALID;
+	NcclApi &n = nccl_api();
+	if (!n.ok) return GPT_E_CUDA;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	if (n.GetUniqueId(&id) != ncclSuccess) return GPT_E_CUDA;
+	memcpy(id128, &id, sizeof(id));
+	return GPT_OK;
+}
+
+int gpt_comm_init(gpt_engine *e, const void *id128, int rank, int world)
+{
+	if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return GPT_E_INVALID;
+	NcclApi &n = nccl_api();
+	if (!n.ok) {
+		e->set_error("gpt_comm_init: libnccl.so.2 not found");
+		return GPT_E_CUDA;
+	}
+	cudaSetDevice(e->device);
+	if (e->comm) {
+		n.CommDestroy(e->comm);
+		e->comm = nullptr;
+	}
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	ncclResult_t r = n.CommInitRank(&e->comm, world, id, rank);
+	if (r != ncclSuccess) {
+		e->set_error(std::string("ncclCommInitRank: ") + n.GetErrorString(r));
+		e->comm = nullptr;
+		return GPT_E_CUDA;
+	}
+	e->comm_rank = rank;
+	e->comm_world = world;
+	return GPT_OK;
+}
+
+int gpt_comm_destroy(gpt_engine *e)
+{
+	if (!e) return GPT_E_INVALID;
+	if (e->comm) {
+		cudaSetDevice(e->device);
+		cudaStreamSynchronize(e->stream);
+		nccl_api().CommDestroy(e->comm);
+		e->comm = nullptr;
+	}
+	e->comm_rank = 0;
+	e->comm_world = 1;
+	return GPT_OK;
+}
+
+int gpt_sampler_run_sharded(gpt_engine *e, int64_t nsteps, int keep, float *ms_per_step)
+{
+	if (!e || !e->sampling || nsteps < 0) return GPT_E_INVALID;
+	SamplerDev &S = e->S;
+	const int H = S.W / 2, world = e->comm_world, rank = e->comm_rank;
+	if (S.nstars != 1) {
+		e->set_error("sampler_run_sharded: one star");
+		return GPT_E_INVALID;
+	}
+	if (world > 1 && (!e->comm || H % world)) {
+		e->set_error("sampler_run_sharded: gpt_comm_init first, and the half-ensemble must divide by the number of ranks");
+		return GPT_E_INVALID;
+	}
+	if (keep && (!S.chain || e->s_kept + nsteps > S.cap)) {
+		e->set_error("sampler_run_sharded: gpt_sampler_reserve first (chain too short)");
+		return GPT_E_INVALID;
+	}
+	cudaSetDevice(e->device);
+	cudaStream_t st = e->stream;
+	NcclApi &n = nccl_api();
+	const int per = H / world, lo = rank * per;
+	std::vector<cudaEvent_t> ev;
+	if (ms_per_step) {
+		ev.resize(2 * nsteps);
+		for (auto &v : ev) CK(cudaEventCreate(&v));
+	}
+	CK(e->s_act.ensure((size_t)S.W));
+	S.act = e->s_act.p;
+	if (!e->d_acc.p) {
+		CK(e->d_acc.ensure(2));
+		CK(cudaMemsetAsync(e->d_acc.p, 0, 2 * sizeof(unsigned long long), st));
+	}
+	for (int64_t s = 0; s < nsteps; s++) {
+		if (ms_per_step) CK(cudaEventRecord(ev[2 * s], st));
+		launch_k(sampler_split_kernel, dim3(1, 1), dim3(256), (size_t)S.W * (sizeof(unsigned long long) + sizeof(int)), st, S, e->s_step);
+		e->n_launch++;
+		for (int half = 0; half < 2; half++) {
+			// every rank proposes for the whole active half (the same Philox stream everywhere) ...
+			launch_k(sampler_propose_kernel, dim3((H + 127) / 128), dim3(128), 0, st, S, e->s_step, half);
+			// ... evaluates its slice of the proposals ...
+			int rc = eval_enqueue(e, e->s_star0, 1, S.q + (size_t)lo * S.ndim, per, S.lq + lo, nullptr, false);
+			if (rc) return rc;
+			// ... the slices are gathered in place over NVLink (the only collective of the path) ...
+			if (world > 1) {
+				ncclResult_t r = n.AllGather(S.lq + lo, S.lq, (size_t)per, ncclDouble, e->comm, st);
+				if (r != ncclSuccess) {
+					e->set_error(std::string("ncclAllGather: ") + n.GetErrorString(r));
+					return GPT_E_CUDA;
+				}
+			}
+			// ... and every rank applies the identical accept/reject
+			launch_k(sampler_accept_kernel, dim3((H + 127) / 128), dim3(128), 0, st, S, e->s_step, half, keep ? e->s_kept : -1LL);
+			e->n_launch += 2;
+		}
+		if (keep) e->s_kept++;
+		e->s_step++;
+		if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
+	}
+	CK(cudaGetLastError());
+	// the verification verdicts of this rank's evaluations steer its halo (one synchronisation per call)
+	unsigned long long acc[2] = {0, 0};
+	CK(cudaMemcpyAsync(acc, e->d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemsetAsync(e->d_acc.p, 0, sizeof(acc), st));
+	CK(cudaStreamSynchronize(st));
+	{
+		double ratio;
+		memcpy(&ratio, &acc[1], sizeof(double));
+		e->last_verr = ratio;
+		if (acc[0]) {
+			e->n_pass2_calls++;
+			e->n_pass2_chunks += (long long)acc[0];
+		}
+		if (e->last_H > 0) e->adapt_halo(e->last_H, acc[0] != 0, ratio);
+	}
+	if (ms_per_step) {
+		for (int64_t s = 0; s < nsteps; s++) CK(cudaEventElapsedTime(&ms_per_step[s], ev[2 * s], ev[2 * s + 1]));
+		for (auto &v : ev) cudaEventDestroy(v);
+	}
 	return GPT_OK;
 }
 

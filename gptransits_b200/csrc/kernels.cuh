@@ -1650,6 +1650,7 @@ struct AcceptPre {
 	size_t gwk;
 	int w;
 	double logu, lpw, fac;
+	double lq_tmp = 0.0;  // (warp-per-walker finalize: lane 0 parks the new log-probability here for the broadcast)
 	double q[2], x[2];  // dimensions lane, lane + 32
 };
 __device__ __forceinline__ void sampler_accept_prefetch(const SamplerDev &S, unsigned long long step, int half, int gi,
@@ -1704,18 +1705,34 @@ __device__ __forceinline__ void sampler_accept_commit(const SamplerDev &S, const
 	}
 }
 
-template <int NT>
-__global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
+// G threads per walker: FIN_THREADS (one block per walker: light curves cut into many chunks, few walkers) or 32
+// (one warp per walker, FINW_WALKERS walkers per block: batches of thousands of walkers cut into a few chunks,
+// where a block per walker costs more in scheduling than the work it does).
+constexpr int FINW_WALKERS = 8;
+template <int NT, int G>
+__global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 {
 	constexpr int J = 2 * NT, NP = J * (J + 1) / 2, CS = NP + J;
+	constexpr bool WARP = G == 32;
+	static_assert(G == 32 || G == FIN_THREADS, "one warp or one block per walker");
 	__shared__ double scratch[FIN_THREADS / 32];
 	__shared__ double s_lp;
-	const int gw = blockIdx.x;
-	const int tid = threadIdx.x, lane = tid & 31;
+	const int gw = WARP ? blockIdx.x * FINW_WALKERS + (threadIdx.x >> 5) : blockIdx.x;
+	const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, lane = threadIdx.x & 31;
+	// sums / votes over the walker's threads
+	auto group_sum = [&](double v) -> double {
+		if (WARP) {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			return v;
+		}
+		return block_sum(v, scratch);
+	};
+	auto group_or = [&](int p) -> int { return WARP ? __any_sync(0xffffffffu, p) : __syncthreads_or(p); };
 	if (gw >= A.nwalk) return;
 	// prologue (before the preceding kernel -- the chunk kernel -- has finished): inputs of the accept/reject,
 	// all written by the prep kernel or earlier
-	const bool acc_warp = A.AC.enabled && (tid >> 5) == FIN_THREADS / 32 - 1;
+	const bool acc_warp = A.AC.enabled && (WARP || (tid >> 5) == FIN_THREADS / 32 - 1);
 	AcceptPre pre;
 	if (acc_warp) sampler_accept_prefetch(A.AC.S, A.AC.step, A.AC.half, gw, lane, pre);
 	pdl_wait();
@@ -1725,6 +1742,7 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 		A.qreset[0] = 0;
 	}
 	if (A.skip_if_clean && (*A.nbad == 0 || !A.wbad[gw])) return;  // second invocation: flagged walkers only
+	constexpr int GS_ = G;  // stride of the walker's threads over chunks
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
 	if ((fl & WF_VALID) && (fl & WF_GENERIC)) return;  // written by gp_generic_kernel
@@ -1749,7 +1767,7 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			ld = A.partial2[gw].logdet;
 		}
 	} else {
-		for (int k = tid; k < A.nchunks; k += FIN_THREADS) {
+		for (int k = tid; k < A.nchunks; k += GS_) {
 			ChunkPartial pr = A.partial[(size_t)gw * A.nchunks + k];
 			q += pr.quad;
 			ld += pr.logdet;
@@ -1772,8 +1790,8 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 		}
 		pr0 = A.partial[(size_t)gw * A.nchunks + k0];
 	}
-	const double quad = block_sum(q, scratch);
-	const double logdet = block_sum(ld, scratch);
+	const double quad = group_sum(q);
+	const double logdet = group_sum(ld);
 	int walker_bad = 0;
 	if (do_verify) {
 		double ua[J];
@@ -1787,7 +1805,7 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 		const double Hh = fmax((double)A.H, 16.0);
 		double worst = 0.0;
 		int nbad = 0;
-		for (int k = k0; k < A.nchunks; k += FIN_THREADS) {
+		for (int k = k0; k < A.nchunks; k += GS_) {
 			if (k != k0) {
 				const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
 				const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
@@ -1844,16 +1862,17 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
 			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
 		}
-		walker_bad = __syncthreads_or(nbad > 0) ? 1 : 0;
+		walker_bad = group_or(nbad > 0) ? 1 : 0;
 		if (walker_bad) {
 			// A flagged chunk is redone exactly from the carry its predecessor left in pass 1.  That carry is as good
 			// as the predecessor's own start after one more chunk of decay: fine when the predecessor passed, and
 			// when it was flagged by a margin the chunk's length makes up for (redo bit 1 clear).  Otherwise
 			// nothing vouches for it and the walker is recomputed whole.
 			int consec = 0;
-			for (int k = k0; k < A.nchunks; k += FIN_THREADS)
+			if (WARP) __syncwarp();
+			for (int k = k0; k < A.nchunks; k += GS_)
 				if (k > 1 && A.redo[(size_t)gw * A.nchunks + k] && (A.redo[(size_t)gw * A.nchunks + k - 1] & 2)) consec = 1;
-			if (__syncthreads_or(consec)) walker_bad = 2;
+			if (group_or(consec)) walker_bad = 2;
 		}
 	}
 	if (tid == 0) {
@@ -1866,19 +1885,26 @@ __global__ void __launch_bounds__(FIN_THREADS) gp_finalize_kernel(FinalArgs A)
 			lnl = -CUDART_INF;
 		}
 		A.lp[gw] = lp;
-		s_lp = lp;
+		if (!WARP) s_lp = lp;
 		if (A.parts) {
 			A.parts[4 * gw + 0] = lnprior;
 			A.parts[4 * gw + 1] = quad;
 			A.parts[4 * gw + 2] = logdet;
 			A.parts[4 * gw + 3] = lnl;
 		}
+		if (WARP) pre.lq_tmp = lp;
 	}
 	if (A.AC.enabled) {
 		// a walker without a flagged chunk is final now; a flagged one is decided by the second
 		// invocation, after pass 2 has repaired its chunks
-		__syncthreads();
-		if (acc_warp && !walker_bad) sampler_accept_commit(A.AC.S, pre, gw, s_lp, A.AC.slot, lane);
+		double lpw;
+		if (WARP) {
+			lpw = __shfl_sync(0xffffffffu, pre.lq_tmp, 0);
+		} else {
+			__syncthreads();
+			lpw = s_lp;
+		}
+		if (acc_warp && !walker_bad) sampler_accept_commit(A.AC.S, pre, gw, lpw, A.AC.slot, lane);
 	}
 }
 

@@ -35,6 +35,7 @@ class Engine:
         self.ndim = None
         self._nstars = 0
         self._N = {}
+        self._comm = None
 
     # -- lifetime
     def close(self):
@@ -197,6 +198,34 @@ class Engine:
 
     def sampler_half_accept(self, half, keep=True):
         self._ck(self._lib.gpt_sampler_half_accept(self._h, int(half), 1 if keep else 0))
+
+    def comm_init(self, dist):
+        """Join the NCCL communicator of the walker-sharded sampler: rank 0 draws the id, torch.distributed (any
+        backend) carries its 128 bytes to the other ranks, every rank joins.  Returns (rank, world)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            self._ck(self._lib.gpt_comm_id(C.cast(buf, C.c_void_p)))
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        tid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(tid, src=0)
+        raw = bytes(tid.cpu().tolist())
+        buf = (C.c_uint8 * 128).from_buffer_copy(raw)
+        self._ck(self._lib.gpt_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+        self._comm = (rank, world)
+        return rank, world
+
+    def comm_destroy(self):
+        self._ck(self._lib.gpt_comm_destroy(self._h))
+        self._comm = None
+
+    def sampler_run_sharded(self, nsteps, keep=True, timed=False):
+        """nsteps with the active half sharded by walker over the communicator of comm_init; everything,
+        the all-gather included, runs on the engine's stream.  timed: -> per-step device milliseconds."""
+        ms = (C.c_float * int(nsteps))() if timed else None
+        self._ck(self._lib.gpt_sampler_run_sharded(self._h, int(nsteps), 1 if keep else 0, ms))
+        return np.array(ms[:], dtype=np.float64) if timed else None
 
     def fp64_peak_tflops(self):
         v = C.c_double()

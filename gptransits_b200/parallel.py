@@ -50,7 +50,7 @@ class _DeviceArray:
                                          "version": 3, "strides": None}
 
 
-def run_walker_sharded(engine, dist, init, nsteps, seed=42, step0=0, a=2.0):
+def run_walker_sharded(engine, dist, init, nsteps, seed=42, step0=0, a=2.0, timed=False, host_collective=False):
     """One star, the ensemble sharded by walker across the ranks of `dist` (NCCL, one process per GPU).
 
     The device-resident form of SURVEY.md section 8e(2): every rank keeps the whole ensemble on its GPU;
@@ -58,14 +58,25 @@ def run_walker_sharded(engine, dist, init, nsteps, seed=42, step0=0, a=2.0):
     proposal log-probabilities are all-gathered in place on the device (the only collective, twice per
     step, a few hundred bytes) and every rank applies the identical accept/reject.  The star must already
     be uploaded (slot 0) on every rank.  Returns (chain[W, nsteps, ndim], logp[nsteps, W]) -- the same
-    on every rank and, up to the evaluation geometry's rounding, the single-GPU sampler's."""
+    on every rank and, up to the evaluation geometry's rounding, the single-GPU sampler's -- and, with
+    timed, the device milliseconds of every step.  host_collective forces the half-step protocol around
+    torch.distributed's all-gather (two host synchronisations per half-step)."""
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
     init = np.asarray(init, dtype=float)
     W = init.shape[0]
     H = W // 2
+    # the whole loop on the engine's stream (the library's own NCCL communicator) when the half-ensemble
+    # divides by the number of ranks; otherwise the half-step calls below around torch's collective
+    on_stream = (world == 1 or (H % world == 0 and dist.get_backend() == "nccl")) and not host_collective
+    if on_stream and world > 1 and getattr(engine, "_comm", None) != (rank, world):
+        engine.comm_init(dist)
     engine.sampler_begin(init, seed=seed, step0=step0, a=a, nstars=1)
     try:
         engine.sampler_reserve(nsteps)
+        if on_stream:
+            ms = engine.sampler_run_sharded(nsteps, keep=True, timed=timed)
+            chain, logp = engine.sampler_read(0, nsteps)
+            return (chain[0], logp[0], ms) if timed else (chain[0], logp[0])
         if world > 1:
             import torch
             ptr, count = engine.sampler_lq_device()

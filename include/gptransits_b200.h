@@ -175,6 +175,15 @@ int gpt_sampler_reserve(gpt_engine *e, int64_t nsteps);
 int gpt_sampler_lq_device(gpt_engine *e, void **lq, int64_t *count);
 int gpt_sampler_half_eval(gpt_engine *e, int half, int lo, int hi);
 int gpt_sampler_half_accept(gpt_engine *e, int half, int keep);
+/* The same with nothing but device work inside a step: the ranks form an NCCL communicator of their own
+ * (gpt_comm_id on one rank -> 128-byte id -> the caller hands it to every rank -> gpt_comm_init on all), and
+ * gpt_sampler_run_sharded enqueues, per half-step and all on the engine's stream, the proposals, this rank's slice
+ * of the posteriors, ncclAllGather of the proposal log-probabilities in place over NVLink, and the accept/reject.
+ * The half-ensemble must divide by the number of ranks.  ms_per_step (may be null): device time of every step. */
+int gpt_comm_id(void *id128);
+int gpt_comm_init(gpt_engine *e, const void *id128, int rank, int world);
+int gpt_comm_destroy(gpt_engine *e);
+int gpt_sampler_run_sharded(gpt_engine *e, int64_t nsteps, int keep, float *ms_per_step);
 int gpt_sampler_end(gpt_engine *e);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------ */

@@ -58,8 +58,12 @@ def _worker(rank, world, port, outdir):
     chain, logp = HalfEnsembleSampler(lambda th: eng.log_prob(th), init, seed=9, dist=dist).run(6)
     np.save(Path(outdir) / f"walker_{rank}.npy", chain)
     # the device-resident form of the same protocol (C ABI half-step calls + NCCL all-gather in place)
+    # (the library's own NCCL communicator: proposals, slice of posteriors, all-gather, accept on one stream)
     dchain, dlogp = run_walker_sharded(eng, dist, init, 6, seed=9)
     np.save(Path(outdir) / f"dwalker_{rank}.npy", dchain)
+    # ... and the half-step calls around torch.distributed's all-gather
+    hchain, hlogp = run_walker_sharded(eng, dist, init, 6, seed=9, host_collective=True)
+    np.save(Path(outdir) / f"hwalker_{rank}.npy", hchain)
     # stars sharded by rank: 3 stars, global ids keep the RNG streams independent of the sharding
     ys = [y + 5.0 * s for s in range(3)]
     inits = np.stack([init] * 3)
@@ -87,6 +91,9 @@ def test_two_gpu_sharding(tmp_path):
     d0, d1 = np.load(tmp_path / "dwalker_0.npy"), np.load(tmp_path / "dwalker_1.npy")
     assert np.array_equal(d0, d1)
     assert np.max(np.abs(d0 - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
+    h0, h1 = np.load(tmp_path / "hwalker_0.npy"), np.load(tmp_path / "hwalker_1.npy")
+    assert np.array_equal(h0, h1)
+    assert np.max(np.abs(h0 - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
     got = {}
     for p in tmp_path.glob("stars_*.npy"):
         lo, hi = map(int, p.stem.split("_")[1:])

@@ -148,3 +148,21 @@ def test_flagged_chunks_are_repaired_whatever_the_geometry(engine):
         engine.set_option("speculate", 1)
         engine.set_option("chunks", 0)
         engine.set_option("halo", 0)
+
+
+def test_sharded_sampler_entry_point_on_one_rank(engine, kic_lc, kic_config):
+    """gpt_sampler_run_sharded with a single rank (no communicator) is the device sampler: the same chain as
+    gpt_sample, step by step -- the all-gather is the only thing more ranks add (tests/test_gpu_multi.py)."""
+    from gptransits_b200.parallel import run_walker_sharded
+    t, f, e = kic_lc
+    gp = GPModel(kic_config["gp"])
+    spec = build_spec(gp, None)
+    np.random.seed(3)
+    init = gp.sample_prior(24)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, (f - 1) * 1e6, e * 1e6)
+    want, wlogp, _ = engine.sample(init, 6, seed=9)
+    chain, logp, ms = run_walker_sharded(engine, None, init, 6, seed=9, timed=True)
+    assert ms.shape == (6,) and np.all(ms > 0)
+    assert rel(chain, want) < 1e-9 and rel(logp, wlogp) < 1e-9
