@@ -10,6 +10,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -95,6 +99,8 @@ struct gpt_engine {
 	long long spec_need_steps = 128;  // clean record needed before a block runs speculatively; doubles on a replay
 	bool spec_last_clean = true;
 	long long n_spec_replays = 0;
+	int opt_async_egress = 1;  // gpt_sample: the chain leaves for the host range by range while the sampler runs
+	long long n_egress_jobs = 0;
 	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
 	int cur_halo = 0;         // 0: derive from the priors at the first evaluation
 	double prior_cmin = 0.0;  // smallest celerite decay rate c the priors allow (rad per megasecond)
@@ -709,6 +715,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 	} else if (k == "speculate") {
 		e->opt_speculate = std::min(2, std::max(0, (int)value));
 		e->spec_last_clean = true;
+	} else if (k == "async_egress") {
+		e->opt_async_egress = value != 0;
 	} else if (k == "pdl") {
 		g_pdl = value != 0;
 	} else if (k == "adapt_every") {
@@ -745,6 +753,7 @@ int gpt_get_stat(gpt_engine *e, const char *key, double *value)
 	else if (k == "pass2_calls") *value = (double)e->n_pass2_calls;
 	else if (k == "pass2_chunks") *value = (double)e->n_pass2_chunks;
 	else if (k == "spec_replays") *value = (double)e->n_spec_replays;
+	else if (k == "egress_jobs") *value = (double)e->n_egress_jobs;
 	else if (k == "evals") *value = (double)e->n_evals;
 	else if (k == "verify_ratio") *value = e->last_verr;
 	else if (k == "chunks") *value = e->last_chunks;
@@ -1134,7 +1143,110 @@ int gpt_sampler_begin(gpt_engine *e, int star0, int nstars, const int32_t *star_
 	return GPT_OK;
 }
 
-static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l2, float *ms_per_step)
+// ---- chain egress (the reference appends every step to its backend, model.py:204-220) ----------
+// Finished step ranges of the device chain leave for the caller's host buffers while the sampler goes on: the
+// sampling stream records an event at the end of a range, a helper thread makes the copy stream wait for it and
+// issues the two strided device-to-host copies there (the caller's buffers are ordinary pageable memory: the
+// copy call blocks its thread, which is why it is not the sampling thread), so only the last range is exposed.
+struct ChainEgress {
+	struct Job {
+		cudaEvent_t ev;
+		int64_t first, count;
+	};
+	gpt_engine *e;
+	double *chain, *logp;  // host [ns][W][total][ndim], [ns][total][W]
+	int64_t total, every;
+	int64_t mark = 0;      // first kept step not yet handed over
+	cudaStream_t cs = nullptr;
+	std::thread th;
+	std::mutex m;
+	std::condition_variable cv;
+	std::deque<Job> q;
+	bool closing = false;
+	cudaError_t err = cudaSuccess;
+	long long njobs = 0;
+
+	ChainEgress(gpt_engine *e_, double *chain_, double *logp_, int64_t total_, int64_t every_)
+		: e(e_), chain(chain_), logp(logp_), total(total_), every(std::max<int64_t>(1, every_))
+	{
+	}
+	cudaError_t start()
+	{
+		cudaError_t r = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+		if (r != cudaSuccess) return r;
+		th = std::thread([this] { loop(); });
+		return cudaSuccess;
+	}
+	void loop()
+	{
+		cudaSetDevice(e->device);
+		for (;;) {
+			Job j;
+			{
+				std::unique_lock<std::mutex> lk(m);
+				cv.wait(lk, [this] { return closing || !q.empty(); });
+				if (q.empty()) return;
+				j = q.front();
+				q.pop_front();
+			}
+			const SamplerDev &S = e->S;
+			const size_t W = S.W, ndim = S.ndim, ns = S.nstars, cap = S.cap;
+			cudaError_t r = cudaStreamWaitEvent(cs, j.ev, 0);
+			if (r == cudaSuccess && chain)
+				r = cudaMemcpy2DAsync(chain + j.first * ndim, total * ndim * sizeof(double), S.chain + j.first * ndim,
+						      cap * ndim * sizeof(double), j.count * ndim * sizeof(double), ns * W,
+						      cudaMemcpyDeviceToHost, cs);
+			if (r == cudaSuccess && logp)
+				r = cudaMemcpy2DAsync(logp + j.first * W, total * W * sizeof(double), S.logp + j.first * W,
+						      cap * W * sizeof(double), j.count * W * sizeof(double), ns, cudaMemcpyDeviceToHost, cs);
+			if (r == cudaSuccess) r = cudaStreamSynchronize(cs);
+			cudaEventDestroy(j.ev);
+			if (r != cudaSuccess) {
+				std::lock_guard<std::mutex> lk(m);
+				if (err == cudaSuccess) err = r;
+			}
+		}
+	}
+	// the kept steps [mark, upto) are final on the sampling stream from this point of its queue on
+	cudaError_t push(cudaStream_t st, int64_t upto)
+	{
+		if (upto <= mark) return cudaSuccess;
+		Job j;
+		cudaError_t r = cudaEventCreateWithFlags(&j.ev, cudaEventDisableTiming);
+		if (r != cudaSuccess) return r;
+		r = cudaEventRecord(j.ev, st);
+		if (r != cudaSuccess) return r;
+		j.first = mark;
+		j.count = upto - mark;
+		mark = upto;
+		{
+			std::lock_guard<std::mutex> lk(m);
+			q.push_back(j);
+			njobs++;
+		}
+		cv.notify_one();
+		return cudaSuccess;
+	}
+	cudaError_t finish()
+	{
+		if (th.joinable()) {
+			{
+				std::lock_guard<std::mutex> lk(m);
+				closing = true;
+			}
+			cv.notify_one();
+			th.join();
+		}
+		if (cs) {
+			cudaStreamDestroy(cs);
+			cs = nullptr;
+		}
+		return err;
+	}
+	~ChainEgress() { finish(); }
+};
+
+static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l2, float *ms_per_step, ChainEgress *eg = nullptr)
 {
 	if (!e || nsteps < 0) return GPT_E_INVALID;
 	if (!e->sampling) {
@@ -1221,6 +1333,8 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 			if (keep) e->s_kept++;
 			if (ms_per_step) CK(cudaEventRecord(ev[2 * s + 1], st));
 			e->s_step++;
+			// a step of a block with its repair pass in line is final once enqueued: hand finished ranges over
+			if (eg && keep && !speculative && (e->s_kept - eg->mark >= eg->every || s + 1 == sb)) CK(eg->push(st, e->s_kept));
 		}
 		CK(cudaGetLastError());
 		return GPT_OK;
@@ -1271,6 +1385,7 @@ static int sampler_run_impl(gpt_engine *e, int64_t nsteps, int keep, int flush_l
 		if (rc) return rc;
 		rc = add_times(sa, sb);
 		if (rc) return rc;
+		if (eg && keep && spec && !flagged) CK(eg->push(st, e->s_kept));  // a speculative block is final once its record is clean
 		e->spec_last_clean = !flagged;
 		if (flagged || e->cur_halo != halo_before) e->spec_clean_steps = 0;
 		else e->spec_clean_steps += sb - sa;
@@ -1668,10 +1783,25 @@ int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, 
 	if (!e || !chain || !logp) return GPT_E_INVALID;
 	int rc = gpt_sampler_begin(e, star0, nstars, nullptr, init, W, seed, step0, a);
 	if (rc) return rc;
-	rc = gpt_sampler_run(e, nsteps, 1);
-	if (rc) return rc;
-	rc = gpt_sampler_read(e, 0, nsteps, chain, logp);
-	if (rc) return rc;
+	// the chain leaves for the caller's buffers range by range while the sampler runs (ranges of at least ~1 KB per
+	// walker row, at most an eighth of the run, so that the strided copies stay efficient and the last one is short)
+	{
+		const int64_t row = std::max<int64_t>(1, 1024 / ((int64_t)e->S.ndim * (int64_t)sizeof(double)));
+		ChainEgress eg(e, chain, logp, nsteps, std::max<int64_t>(row, (nsteps + 7) / 8));
+		if (e->opt_async_egress) CK(eg.start());
+		rc = sampler_run_impl(e, nsteps, 1, 0, nullptr, e->opt_async_egress ? &eg : nullptr);
+		cudaError_t er = eg.finish();
+		if (rc) return rc;
+		if (er != cudaSuccess) {
+			e->set_error(std::string("chain egress: ") + cudaGetErrorString(er));
+			return GPT_E_CUDA;
+		}
+		if (!e->opt_async_egress || eg.mark < nsteps) {
+			rc = gpt_sampler_read(e, 0, nsteps, chain, logp);
+			if (rc) return rc;
+		}
+		e->n_egress_jobs = eg.njobs;
+	}
 	if (naccept) {
 		rc = gpt_sampler_state(e, nullptr, nullptr, naccept);
 		if (rc) return rc;

@@ -14,6 +14,7 @@ from pathlib import Path
 
 import numpy as np
 
+from .chainstore import ChainStore
 from .config import load_config
 from .convergence import gelman_brooks, gelman_rubin, geweke
 from .engine import Engine
@@ -168,28 +169,34 @@ class Model:
     def _state_file(self):
         return self.datadir / "chain_state.npz"
 
+    def _store(self):
+        """Append-only checkpoints under <datadir>/chain_state/ (a legacy chain_state.npz is read as block 0)."""
+        return ChainStore(self.datadir / "chain_state", legacy=self._state_file())
+
     def run(self, reset=False, num_threads=1):
         eng = self._ensure_engine()
         nwalkers = self.settings.get("num_walkers") or 4 * self.ndim      # model.py:230
         nsteps = int(self.settings["num_steps"])
         save = bool(self.settings["save"])
         done, chain0, logp0, init = 0, None, None, None
-        state = self._state_file()
+        store = self._store() if save else None
         if save:
             self.datadir.mkdir(parents=True, exist_ok=True)
-            if state.is_file():
+            if store.exists():
                 if reset:
                     log.info("Resetting the backend sampler")
-                    state.unlink()
+                    store.reset()
                 else:
-                    with np.load(state) as z:
-                        done, chain0, logp0 = int(z["iteration"]), z["chain"], z["log_prob"]
-                    if done >= nsteps:
-                        log.warning("Skipping run. Backend number of iterations greater than settings")
+                    st = store.load()
+                    done, chain0, logp0 = st["iteration"], st["chain"], st["log_prob"]
+                    if done >= nsteps or st["converged"]:
+                        log.warning("Skipping run. Backend number of iterations greater than settings"
+                                    if done >= nsteps else "Skipping run. The stored run stopped on its rhat_stop criterion")
                         self.chain, self.log_prob = chain0, logp0
                         return
-                    init = chain0[:, -1, :]
-                    nwalkers = chain0.shape[0]
+                    if chain0 is not None:
+                        init = chain0[:, -1, :]
+                        nwalkers = chain0.shape[0]
         if init is None:
             init = self.sample_initial(nwalkers)
         remaining = nsteps - done
@@ -208,6 +215,7 @@ class Model:
                 logps.append(l[0])
                 remaining -= n
                 done += n
+                converged = False
                 if n >= 4:
                     # Gelman-Rubin V/W of this block, computed on the device-resident chain
                     rhat = eng.sampler_rhat(0, n)[0]
@@ -217,12 +225,15 @@ class Model:
                     if stop and rhat.max() < stop:
                         log.info(f"stopping early: V/W below {stop}")
                         remaining = 0
+                        converged = True
                 if save:
-                    np.savez(state, iteration=done, chain=np.concatenate(chains, axis=1),
-                             log_prob=np.concatenate(logps, axis=0))
+                    # the block goes to disk on the store's thread while the next one is sampled
+                    store.append(done - n, c[0], l[0], done, converged)
             _, _, nacc = eng.sampler_state()
         finally:
             eng.sampler_end()
+            if store is not None:
+                store.close()
         self.chain = np.concatenate(chains, axis=1)          # (W, nsteps, ndim)   model.py:283
         self.log_prob = np.concatenate(logps, axis=0)        # (nsteps, W)         model.py:284
         self.acceptance_fraction = nacc[0] / max(1, self.chain.shape[1] - (chain0.shape[1] if chain0 is not None else 0))

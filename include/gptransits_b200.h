@@ -88,7 +88,8 @@ const char *gpt_version(void);
  * "fuse_scan" (epoch scan inside the prep kernel for small batches, default 1), "transit_strict" (batman's
  * operation order), "series_order_min" (0..4: lowest treatment of regular-cadence steps, 4 = general loop),
  * "pdl" (programmatic dependent launch, default 0), "speculate" (sampler blocks without repair launches,
- * replayed when a chunk was flagged: 0 never, 1 after a long clean record -- default --, 2 eagerly), "time_kernels", "reset_timers".
+ * replayed when a chunk was flagged: 0 never, 1 after a long clean record -- default --, 2 eagerly), "async_egress"
+ * (gpt_sample streams finished step ranges of the chain to the host while sampling, default 1), "time_kernels", "reset_timers".
  * Counters: "launches", "evals", "pass2_chunks", "spec_replays", "verify_ratio", "halo", "chunks", "chunk_len",
  * "transit_items", "ms_<kernel>" / "n_<kernel>" for prep, transit, trscan, chunk, final, pass2. */
 int gpt_set_option(gpt_engine *e, const char *key, double value);
@@ -147,7 +148,10 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
  *   naccept [nstars][W] (optional)
  * step0 is the number of iterations already done (resume, model.py:235-253):
  * the Philox stream is keyed by (seed, star id, step0 + i, walker) so results
- * do not depend on how the run is split or on the number of GPUs.  Every step is kept. */
+ * do not depend on how the run is split or on the number of GPUs.  Every step is kept.
+ * chain and logp are ordinary host buffers; finished ranges of steps are copied into them on a second
+ * stream while the sampler runs (the reference appends every step to its backend, model.py:204-220), so
+ * only the last range's copy is exposed. */
 int gpt_sample(gpt_engine *e, int star0, int nstars, const double *init, int W, int64_t nsteps,
 	       uint64_t seed, uint64_t step0, double a, double *chain, double *logp, int64_t *naccept);
 

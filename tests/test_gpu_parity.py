@@ -356,6 +356,9 @@ def test_model_surface_runs_kic_example(kic_lc, kic_config, tmp_path):
     m2.run()
     assert m2.chain.shape == (24, 60, 6)
     assert np.array_equal(m2.chain[:, :40], m.chain)
+    # append-only checkpoints: 25 + 15 steps of the first run, 20 of the second, each block written once
+    blocks = sorted(p.name for p in (tmp_path / "data" / "chain_state").glob("block_*.npz"))
+    assert blocks == ["block_000000.npz", "block_000001.npz", "block_000002.npz"]
     stats = m2.statistics()
     assert stats["params"]["median"].shape == (6,)
     m.close()

@@ -166,3 +166,33 @@ def test_sharded_sampler_entry_point_on_one_rank(engine, kic_lc, kic_config):
     chain, logp, ms = run_walker_sharded(engine, None, init, 6, seed=9, timed=True)
     assert ms.shape == (6,) and np.all(ms > 0)
     assert rel(chain, want) < 1e-9 and rel(logp, wlogp) < 1e-9
+
+
+def test_chain_egress_while_sampling_equals_the_read_at_the_end(engine, kic_lc, kic_config):
+    """gpt_sample streams finished step ranges to the host buffers on a second stream while the sampler runs
+    (SURVEY.md 8 f3); the result is the chain a single read at the end returns -- with the repair pass in line
+    and with speculative blocks (which are handed over only once their record is clean)."""
+    t, f, e = kic_lc
+    gp = GPModel(kic_config["gp"])
+    spec = build_spec(gp, None)
+    np.random.seed(5)
+    init = gp.sample_prior(24)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, (f - 1) * 1e6, e * 1e6)
+    try:
+        engine.set_option("halo", 640)   # a fixed geometry: the runs below are then bit-identical
+        engine.set_option("chunks", 4)
+        engine.set_option("async_egress", 0)
+        want, wlogp, wacc = engine.sample(init, 150, seed=11)
+        for speculate in (1, 2):
+            engine.set_option("async_egress", 1)
+            engine.set_option("speculate", speculate)
+            chain, logp, nacc = engine.sample(init, 150, seed=11)
+            assert engine.stat("egress_jobs") >= 2
+            assert np.array_equal(chain, want) and np.array_equal(logp, wlogp) and np.array_equal(nacc, wacc)
+    finally:
+        engine.set_option("speculate", 1)
+        engine.set_option("async_egress", 1)
+        engine.set_option("halo", 0)
+        engine.set_option("chunks", 0)

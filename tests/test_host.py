@@ -197,3 +197,40 @@ def test_bench_reference_arm_prints_one_json_line():
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert key in d
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_chain_store_appends_blocks_and_resumes(tmp_path):
+    """The checkpoint store: blocks are written once each, the state survives a reload,
+    a legacy single-file checkpoint is read as the first block, and nothing is left half-written."""
+    from gptransits_b200.chainstore import ChainStore
+    rng = np.random.default_rng(0)
+    W, ndim = 6, 3
+    legacy = tmp_path / "chain_state.npz"
+    c0, l0 = rng.normal(size=(W, 5, ndim)), rng.normal(size=(5, W))
+    np.savez(legacy, iteration=5, chain=c0, log_prob=l0)
+    store = ChainStore(tmp_path / "chain_state", legacy=legacy)
+    assert store.exists()
+    st = store.load()
+    assert st["iteration"] == 5 and np.array_equal(st["chain"], c0) and not st["converged"]
+    blocks = [(rng.normal(size=(W, n, ndim)), rng.normal(size=(n, W))) for n in (4, 7, 2)]
+    it = 5
+    for k, (c, l) in enumerate(blocks):
+        store.append(it, c, l, it + c.shape[1], converged=(k == 2))
+        it += c.shape[1]
+    store.close()
+    names = sorted(p.name for p in (tmp_path / "chain_state").iterdir())
+    assert names == ["block_000000.npz", "block_000001.npz", "block_000002.npz", "state.json"]
+    mtimes = {n: (tmp_path / "chain_state" / n).stat().st_mtime_ns for n in names[:2]}
+    st = ChainStore(tmp_path / "chain_state", legacy=legacy).load()
+    assert st["iteration"] == 18 and st["converged"]
+    assert np.array_equal(st["chain"], np.concatenate([c0] + [b[0] for b in blocks], axis=1))
+    assert np.array_equal(st["log_prob"], np.concatenate([l0] + [b[1] for b in blocks], axis=0))
+    # a later append touches only the new block and the state file
+    store = ChainStore(tmp_path / "chain_state", legacy=legacy)
+    store.append(18, blocks[0][0], blocks[0][1], 22)
+    store.close()
+    for n, m in mtimes.items():
+        assert (tmp_path / "chain_state" / n).stat().st_mtime_ns == m
+    assert ChainStore(tmp_path / "chain_state", legacy=legacy).load()["iteration"] == 22
+    store.reset()
+    assert not store.exists()
