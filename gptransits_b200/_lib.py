@@ -85,6 +85,7 @@ SIGNATURES = {
     "gpt_get_stat": (C.c_int, [_vp, C.c_char_p, _dp]),
     "gpt_model_set": (C.c_int, [_vp, C.POINTER(ModelDesc)]),
     "gpt_star_upload": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int64]),
+    "gpt_stars_upload": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64]),
     "gpt_star_clear": (C.c_int, [_vp]),
     "gpt_log_prob": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "gpt_log_prob_multi": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),

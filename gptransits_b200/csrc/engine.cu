@@ -59,7 +59,7 @@ struct DevBuf {
 
 struct Star {
 	char *blob = nullptr;     // one allocation per star (samp | tdays | tile_dt0 | irr), reused by re-uploads that fit
-	size_t blob_cap = 0;
+	size_t blob_cap = 0, blob_used = 0;
 	double4 *samp = nullptr;
 	double *tdays = nullptr;
 	int *irr = nullptr;
@@ -111,7 +111,9 @@ struct gpt_engine {
 	int last_chunks = 0, last_L = 0, last_H = 0;
 
 	// evaluation workspaces
-	DevBuf<double> d_theta, d_lp, d_parts, d_prep, d_mean, d_carryT, d_carryE;
+	DevBuf<double> d_theta, d_lp, d_parts, d_prep, d_mean, d_carryT, d_carryE, d_yup;
+	DevBuf<double> d_zero;  // [1] 0.0: what the chunk kernel reads for a sample outside the transit window
+	DevBuf<unsigned int> d_winmask;  // [nwalk][ceil(N/32)] in-window bits of the transit model
 	DevBuf<int> d_flags, d_wstatus, d_wbad;
 	DevBuf<ChunkPartial> d_partial;
 	DevBuf<ChunkPartial> d_partial2;  // [nwalk] results of the sequential recomputation of flagged walkers
@@ -362,13 +364,13 @@ static size_t scan_smem_bytes(int N)
 // flux of the queued (walker, sample) items; "transit_strict" selects batman's own operation order
 static void launch_transit_eval(gpt_engine *e, cudaStream_t st, const StarDev *stars, int W, int ss, double exp_time,
 				int mode, const double *prep, const unsigned long long *queue, const unsigned int *qcount,
-				double *out, int dense)
+				double *out, int dense, unsigned int *winmask = nullptr, int nw32 = 0)
 {
 	const int grid = e->num_sms * 2 * TR_MINBLOCKS;
 	if (e->opt_transit_strict)
-		launch_k(transit_eval_kernel<true>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+		launch_k(transit_eval_kernel<true>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense, winmask, nw32);
 	else
-		launch_k(transit_eval_kernel<false>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense);
+		launch_k(transit_eval_kernel<false>, dim3(grid), dim3(TR_THREADS), 0, st, stars, W, ss, exp_time, mode, prep, queue, qcount, out, dense, winmask, nw32);
 }
 
 // threads per chunk CTA: one per walker of the star, a whole number of warps, at most 128
@@ -441,6 +443,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	const int N = e->stars[star0].N;
 	const int nwalk = nstars * W;
 	const int nt = m.nterms;
+	const int nw32 = 4 * ((N + 127) / 128);  // in-window mask: four 32-bit words per 128-sample tile (rows 16-byte aligned)
 	const StarDev *dst = e->d_stars.p + star0;
 	cudaStream_t st = e->stream;
 
@@ -457,7 +460,13 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 		CK(e->d_mean.ensure((size_t)nwalk * N));
 		CK(e->d_queue.ensure((size_t)nwalk * N));
 		CK(e->d_qcount.ensure(1));
+		if (nt > 0) CK(e->d_winmask.ensure((size_t)nwalk * nw32));
+		if (!e->d_zero.p) {
+			CK(e->d_zero.ensure(1));
+			CK(cudaMemsetAsync(e->d_zero.p, 0, sizeof(double), st));
+		}
 	}
+	unsigned int *winmask = (m.has_transit && nt > 0) ? e->d_winmask.p : nullptr;
 
 	// small batches: the epoch scan rides on the prep kernel (one launch, the window never leaves the CTA)
 	const bool fuse_scan = m.has_transit && nwalk <= 1024 && e->opt_epoch_scan && e->opt_fuse_scan;
@@ -486,6 +495,8 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	sc.items_cap = scan_items_cap(N);
 	sc.queue = e->d_queue.p;
 	sc.qcount = qcount;
+	sc.winmask = fuse_scan ? winmask : nullptr;  // cleared by whichever kernel runs the scan
+	sc.nw32 = nw32;
 	if (nwalk <= 4096)
 		launch_k(prep_kernel, dim3(nwalk), dim3(prep_threads), fuse_scan ? scan_smem_bytes(N) : 0, st, m, dst, W, d_theta, nwalk,
 			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
@@ -503,16 +514,16 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 				int et = 32;
 				while (et < TR_THREADS && et * 256 < N) et *= 2;
 				launch_k(transit_epoch_scan_kernel, dim3(nwalk), dim3(et), scan_smem_bytes(N), st, dst, W, e->d_prep.p, e->d_flags.p,
-					 e->d_queue.p, qcount, scan_items_cap(N));
+					 e->d_queue.p, qcount, scan_items_cap(N), winmask, nw32);
 			} else {
 				launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, W, e->d_prep.p, e->d_flags.p, e->d_queue.p, qcount,
-					 e->d_mean.p, 0);
+					 e->d_mean.p, 0, winmask, nw32);
 			}
 			e->timer_end(TK_TRSCAN);
 			e->n_launch++;
 		}
 		launch_transit_eval(e, st, dst, W, m.supersample, m.exp_time, m.ellip_mode, e->d_prep.p, e->d_queue.p, qcount,
-				    e->d_mean.p, 0);
+				    e->d_mean.p, 0, winmask, nw32);
 		e->timer_end(TK_TRANSIT);
 		e->n_launch++;
 	}
@@ -545,6 +556,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 
 	ChunkArgs a;
 	a.stars = dst; a.prep = e->d_prep.p; a.flags = e->d_flags.p; a.mean = e->d_mean.p;
+	a.winmask = winmask; a.nw32 = nw32; a.zero = e->d_zero.p;
 	a.carryT = e->d_carryT.p; a.carryE = e->d_carryE.p; a.partial = e->d_partial.p;
 	a.wstatus = e->d_wstatus.p; a.redo = e->d_redo.p; a.nbad = e->d_nbad.p; a.wbad = e->d_wbad.p; a.partial2 = e->d_partial2.p;
 	a.W = W; a.N = N; a.nchunks = nchunks; a.L = L; a.H = H; a.pass2 = 0;
@@ -680,7 +692,7 @@ void gpt_engine_destroy(gpt_engine *e)
 	cudaStreamSynchronize(e->stream);
 	gpt_star_clear(e);
 	e->d_stars.release();
-	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release();
+	e->d_theta.release(); e->d_lp.release(); e->d_parts.release(); e->d_prep.release(); e->d_mean.release(); e->d_yup.release(); e->d_winmask.release(); e->d_zero.release();
 	e->d_carryT.release(); e->d_carryE.release(); e->d_flags.release(); e->d_wstatus.release();
 	e->d_partial.release(); e->d_partial2.release(); e->d_redo.release(); e->d_nbad.release(); e->d_verr.release(); e->d_acc.release();
 	e->d_queue.release(); e->d_qcount.release(); e->d_qfused.release(); e->d_wbad.release();
@@ -1010,6 +1022,7 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 		CK(cudaMalloc((void **)&s.blob, total));
 		s.blob_cap = total;
 	}
+	s.blob_used = total;
 	s.samp = reinterpret_cast<double4 *>(s.blob + off_samp);
 	s.tdays = reinterpret_cast<double *>(s.blob + off_tdays);
 	s.tile_dt0 = reinterpret_cast<double *>(s.blob + off_tile);
@@ -1018,6 +1031,61 @@ int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double 
 	CK(cudaStreamSynchronize(e->stream));
 	e->stars_dirty = true;
 	e->spec_clean_steps = 0;  // new data: the clean record of the speculative sampler starts over
+	return GPT_OK;
+}
+
+// Many stars on one time grid (a survey batch: SURVEY.md 8 e1).  The grid is analysed once (gpt_star_upload of the
+// first star); the other stars receive a device-to-device copy of its blob and their own fluxes, which cross the
+// bus as one [nstars-1][N] matrix and are scattered into the samples by a kernel.
+__global__ void star_fill_y_kernel(const StarDev *stars, int nstars, int N, const double *y)
+{
+	const int s = blockIdx.y;
+	double4 *samp = const_cast<double4 *>(stars[s].samp);
+	for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) samp[n].y = y[(size_t)s * N + n];
+}
+
+int gpt_stars_upload(gpt_engine *e, int star0, int nstars, const double *t_days, const double *y, const double *yerr, int64_t N)
+{
+	if (!e || !t_days || !y || nstars < 1 || star0 < 0) return GPT_E_INVALID;
+	int rc = gpt_star_upload(e, star0, t_days, y, yerr, N);
+	if (rc || nstars == 1) return rc;
+	cudaSetDevice(e->device);
+	if ((size_t)(star0 + nstars) > e->stars.size()) e->stars.resize(star0 + nstars);
+	const Star proto = e->stars[star0];
+	const size_t total = proto.blob_used;
+	for (int i = 1; i < nstars; i++) {
+		Star &d = e->stars[star0 + i];
+		if (d.blob_cap < total) {
+			if (d.blob) cudaFree(d.blob);
+			d.blob = nullptr;
+			d.blob_cap = 0;
+			CK(cudaMalloc((void **)&d.blob, total));
+			d.blob_cap = total;
+		}
+		d.blob_used = total;
+		d.samp = reinterpret_cast<double4 *>(d.blob + ((char *)proto.samp - proto.blob));
+		d.tdays = reinterpret_cast<double *>(d.blob + ((char *)proto.tdays - proto.blob));
+		d.tile_dt0 = reinterpret_cast<double *>(d.blob + ((char *)proto.tile_dt0 - proto.blob));
+		d.irr = reinterpret_cast<int *>(d.blob + ((char *)proto.irr - proto.blob));
+		d.nirr = proto.nirr;
+		d.N = proto.N;
+		d.dt0 = proto.dt0;
+		d.dreg = proto.dreg;
+		d.dmax = proto.dmax;
+		d.cdev = proto.cdev;
+		d.has_err = proto.has_err;
+		CK(cudaMemcpyAsync(d.blob, proto.blob, total, cudaMemcpyDeviceToDevice, e->stream));
+	}
+	CK(e->d_yup.ensure((size_t)(nstars - 1) * N));
+	CK(cudaMemcpyAsync(e->d_yup.p, y + N, sizeof(double) * (size_t)(nstars - 1) * N, cudaMemcpyHostToDevice, e->stream));
+	e->stars_dirty = true;
+	rc = sync_stars(e);
+	if (rc) return rc;
+	star_fill_y_kernel<<<dim3((unsigned)std::min<int64_t>((N + 255) / 256, 64), nstars - 1), 256, 0, e->stream>>>(
+		e->d_stars.p + star0 + 1, nstars - 1, (int)N, e->d_yup.p);
+	e->n_launch++;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(e->stream));
 	return GPT_OK;
 }
 
@@ -1084,7 +1152,7 @@ int gpt_transit_flux(gpt_engine *e, int star, const double *pars9, int W, double
 									    e->d_flags.p);
 	dim3 g(W, (N + TR_THREADS - 1) / TR_THREADS);
 	launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, e->stream, e->d_stars.p + star, W, e->d_prep.p, e->d_flags.p, e->d_queue.p,
-							     e->d_qcount.p, e->d_mean.p, 1);
+							     e->d_qcount.p, e->d_mean.p, 1, (unsigned int *)nullptr, 0);
 	launch_transit_eval(e, e->stream, e->d_stars.p + star, W, e->model.supersample,
 								   e->model.exp_time, e->model.ellip_mode, e->d_prep.p,
 								   e->d_queue.p, e->d_qcount.p, e->d_mean.p, 1);
@@ -1860,7 +1928,7 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);
 		launch_k(transit_scan_kernel, dim3(g), dim3(TR_THREADS), 0, st, dst, 1, e->d_prep.p, e->d_flags.p, e->d_queue.p, e->d_qcount.p,
-							      e->d_mean.p, 0);
+							      e->d_mean.p, 0, (unsigned int *)nullptr, 0);
 		launch_transit_eval(e, st, dst, 1, m.supersample, m.exp_time, m.ellip_mode,
 										e->d_prep.p, e->d_queue.p, e->d_qcount.p, e->d_mean.p, 0);
 	}

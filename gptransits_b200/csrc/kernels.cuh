@@ -225,6 +225,8 @@ struct PrepScan {
 	int items_cap;
 	unsigned long long *queue;
 	unsigned int *qcount;
+	unsigned int *winmask;  // [nwalk][nw32] in-window bit of every sample (set by the flux kernel): cleared here
+	int nw32;
 };
 __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
 				  unsigned int *qcount, int items_cap);
@@ -247,6 +249,8 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 	}
 	if (gw >= nwalk) return;
 	if (tid == 0 && R.wstatus) R.wstatus[gw] = 0;
+	if (SC.winmask)
+		for (int i = tid; i < SC.nw32; i += blockDim.x) SC.winmask[(size_t)gw * SC.nw32 + i] = 0u;
 	double *pp = prep + (size_t)gw * PREP_STRIDE;
 	const StarDev st = stars[gw / W];
 
@@ -557,7 +561,7 @@ constexpr int TR_THREADS = 256;
 
 __global__ void __launch_bounds__(TR_THREADS)
 transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
-		    unsigned int *qcount, double *out, int dense)
+		    unsigned int *qcount, double *out, int dense, unsigned int *winmask, int nw32)
 {
 	pdl_wait();
 	pdl_trigger();
@@ -567,6 +571,7 @@ transit_scan_kernel(const StarDev *stars, int W, const double *prep, const int *
 	const StarDev st = stars[gw / W];
 	const int N = st.N;
 	const int n = blockIdx.y * TR_THREADS + threadIdx.x;
+	if (winmask && n < N && (n & 31) == 0) winmask[(size_t)gw * nw32 + (n >> 5)] = 0u;
 	const double *pp = prep + (size_t)gw * PREP_STRIDE;
 	TransitPars tr;
 	tr.per = pp[PP_TR + 0];
@@ -833,11 +838,13 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 
 __global__ void __launch_bounds__(TR_THREADS)
 transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const int *flags, unsigned long long *queue,
-			  unsigned int *qcount, int items_cap)
+			  unsigned int *qcount, int items_cap, unsigned int *winmask, int nw32)
 {
 	pdl_wait();
 	pdl_trigger();
 	const int gw = blockIdx.x;
+	if (winmask)
+		for (int i = threadIdx.x; i < nw32; i += blockDim.x) winmask[(size_t)gw * nw32 + i] = 0u;
 	const int fl = flags[gw];
 	if (!(fl & WF_VALID)) return;
 	const StarDev st = stars[gw / W];
@@ -851,7 +858,8 @@ transit_epoch_scan_kernel(const StarDev *stars, int W, const double *prep, const
 template <bool STRICT>
 __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS)
 transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mode, const double *prep,
-		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense)
+		    const unsigned long long *queue, const unsigned int *qcount, double *out, int dense, unsigned int *winmask,
+		    int nw32)
 {
 	pdl_wait();
 	pdl_trigger();
@@ -895,6 +903,8 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 				double m = ss > 1 ? s / ss : s;
 				if (inverse) m = 2.0 - m;  // batman: rp < 0 is an inverse transit, light curve 2 - lc
 				out[(size_t)gw * N + n] = dense ? m : (m - 1) * 1e6;  // transit.py:127
+				// the sample's in-window bit: the chunk kernel reads the model exactly where it was written
+				if (winmask) atomicOr(&winmask[(size_t)gw * nw32 + (n >> 5)], 1u << (n & 31));
 			}
 		}
 	} else {
@@ -912,6 +922,7 @@ transit_eval_kernel(const StarDev *stars, int W, int ss, double exp_time, int mo
 			double m = s / ss;
 			if (tr.inverse) m = 2.0 - m;
 			out[(size_t)gw * st.N + n] = dense ? m : (m - 1) * 1e6;
+			if (winmask) atomicOr(&winmask[(size_t)gw * nw32 + (n >> 5)], 1u << (n & 31));
 		}
 	}
 }
@@ -922,6 +933,9 @@ struct ChunkArgs {
 	const double *prep;
 	const int *flags;
 	const double *mean;       // [nwalk][N] transit model (ppm), valid inside each walker's window
+	const unsigned int *winmask;  // [nwalk][nw32] bit n: mean[n] was written (the sample is in the walker's window)
+	int nw32;
+	const double *zero;       // [1] 0.0
 	double *carryT;           // [nwalk][nchunks][CS]  exact carry entering chunk k (written by chunk k-1)
 	double *carryE;           // [nwalk][nchunks][CS]  halo estimate of the same
 	ChunkPartial *partial;    // [nwalk][nchunks]
@@ -1352,28 +1366,35 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		pdl_wait();
 		pdl_trigger();
 	}
-	if (TRANSIT && meanw) {
-		prefetch_l1(meanw + hs);
-		prefetch_l1(meanw + min(hs + 16, N - 1));
-	}
-	// residual of sample m: flux minus this walker's transit model.  The model array is valid only
-	// inside the walker's window, so it is loaded unconditionally (L1-prefetched line by line, and ahead
-	// of its use in the fast loop) and selected.  (A load predicated on the window test was measured
-	// slower: the divergent branch and the extra shared-memory read cost more than the loads save.)
+	// Transit model of sample m: 0 outside the walker's window.  The flux kernel wrote the model for the in-window
+	// samples only and set their bits in the walker's mask row; the bit predicates the load, so the ~96 % of the
+	// samples out of transit cost one shift and no memory traffic, and no window arithmetic runs on the FP64 pipe.
+	// m never decreases along a chunk (and is uniform over the CTA): the current and the next 32-sample word of
+	// the row sit in registers, the next one requested 32 steps before its first use.
+	static_assert(TILE == 128, "the mask of one tile is four 32-bit words");
+	const uint4 *mrow = (TRANSIT && meanw) ? reinterpret_cast<const uint4 *>(A.winmask + (size_t)gw * A.nw32) : nullptr;
+	unsigned long long mlo = 0ull, mhi = 0ull;   // bits of the current tile's samples 0..63, 64..127
+	uint4 mnext = make_uint4(0u, 0u, 0u, 0u);    // the next tile's, in flight
+	auto mask_tile = [&](int tl, bool first) {   // at the start of tile tl (straight-line code: no branch in the step loop)
+		if (TRANSIT && meanw) {
+			const uint4 cur = first ? mrow[tl] : mnext;
+			mnext = mrow[min(tl + 1, A.nw32 / 4 - 1)];
+			mlo = ((unsigned long long)cur.y << 32) | cur.x;
+			mhi = ((unsigned long long)cur.w << 32) | cur.z;
+		}
+	};
 	const double4 *tile = nullptr;
 	auto load_mean = [&](int m) -> double {
 		double mv = 0.0;
 		if (TRANSIT && meanw) {
-			mv = meanw[m];
-			if ((m & 15) == 0) prefetch_l1(meanw + min(m + 48, N - 1));
+			// always a load (the loop is scheduled around one): out of the window it reads a zero every lane shares
+			const unsigned long long q = (m & 64) ? mhi : mlo;
+			const double *src = ((q >> (m & 63)) & 1ull) ? meanw + m : A.zero;
+			mv = *src;
 		}
 		return mv;
 	};
-	auto residual_mv = [&](const double4 &sm, double mv) -> double {
-		double y = sm.y;
-		if (TRANSIT) y -= in_transit_window(sm.w, wcen, inv_per, whalf) ? mv : 0.0;
-		return y;
-	};
+	auto residual_mv = [&](const double4 &sm, double mv) -> double { return TRANSIT ? sm.y - mv : sm.y; };
 	auto residual = [&](const double4 &sm, int m) -> double { return residual_mv(sm, load_mean(m)); };
 	auto store_carry = [&](double *dst) {
 #pragma unroll
@@ -1391,6 +1412,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 		mbar_wait(&s_bar[stg], (uint32_t)((it / NSTAGE) & 1));
 		const int s0 = max(tl * TILE, hs), s1 = min((tl + 1) * TILE, n1);
 		tile = &s_tile[stg][0] - tl * TILE;
+		mask_tile(tl, tl == t_first);
 		const bool store_here = (!pass2 && c > 0 && active && n0 >= s0 && n0 < s1);
 		double *const cdst = A.carryE + ((size_t)gw * A.nchunks + c) * CS;
 

@@ -99,6 +99,18 @@ class Engine:
         self._N[int(star)] = t.size
         self._nstars = max(self._nstars, int(star) + 1)
 
+    def upload_stars(self, star0, t_days, ys, yerr=None):
+        """Stars star0 .. star0+len(ys)-1 observed on one time grid: ys [nstars, N], one yerr for all."""
+        t, ys = _d(t_days), _d(ys)
+        if ys.ndim != 2 or t.ndim != 1 or ys.shape[1] != t.size:
+            raise ValueError("ys must be [nstars, N] on the time grid t_days [N]")
+        e = None if yerr is None else _d(np.broadcast_to(yerr, t.shape))
+        self._ck(self._lib.gpt_stars_upload(self._h, int(star0), ys.shape[0], _p(t), _p(ys),
+                                            _p(e) if e is not None else None, t.size))
+        for s in range(int(star0), int(star0) + ys.shape[0]):
+            self._N[s] = t.size
+        self._nstars = max(self._nstars, int(star0) + ys.shape[0])
+
     def clear_stars(self):
         self._ck(self._lib.gpt_star_clear(self._h))
         self._N = {}

@@ -106,6 +106,10 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *desc);
  * reference: ppm).  yerr == NULL -> celerite's default 1.123e-12. */
 int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double *y,
 		    const double *yerr, int64_t N);
+/* The same for nstars stars observed on ONE time grid with one error array (a survey batch, slots star0 ..
+ * star0+nstars-1): y [nstars][N].  The grid is analysed once and only the fluxes cross the bus per star. */
+int gpt_stars_upload(gpt_engine *e, int star0, int nstars, const double *t_days, const double *y,
+		     const double *yerr, int64_t N);
 int gpt_star_clear(gpt_engine *e);
 
 /* ---- posterior seam ----------------------------------------------------- */

@@ -196,3 +196,33 @@ def test_chain_egress_while_sampling_equals_the_read_at_the_end(engine, kic_lc, 
         engine.set_option("async_egress", 1)
         engine.set_option("halo", 0)
         engine.set_option("chunks", 0)
+
+
+def test_batch_upload_on_one_grid_equals_star_by_star(engine):
+    """gpt_stars_upload (one time grid, fluxes as a matrix) leaves the engine in the state the per-star uploads
+    leave it in: identical log-probabilities, also after one star of the batch is replaced on its own."""
+    from gptransits_b200 import synth
+    np.random.seed(8)
+    gp = GPModel(synth.c3_config()["gp"])
+    spec = build_spec(gp, None)
+    t, y, yerr, th = synth.make_stars(6, 2048, seed0=77)
+    theta = gp.sample_prior(6 * 8).reshape(6, 8, -1)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.set_option("chunks", 1)   # one geometry for every call below: the comparisons are then bit for bit
+    try:
+        for s in range(6):
+            engine.upload_star(s, t, y[s], yerr)
+        want = engine.log_prob(theta, star=0, nstars=6)
+        assert np.all(np.isfinite(want))
+        engine.clear_stars()
+        engine.upload_stars(0, t, y, yerr)
+        got = engine.log_prob(theta, star=0, nstars=6)
+        assert np.array_equal(got, want)
+        engine.upload_star(3, t, y[0], yerr)
+        got3 = engine.log_prob(theta[3:4], star=3, nstars=1)
+        engine.clear_stars()
+        engine.upload_star(0, t, y[0], yerr)
+        assert np.array_equal(got3, engine.log_prob(theta[3:4], star=0, nstars=1))
+    finally:
+        engine.set_option("chunks", 0)
