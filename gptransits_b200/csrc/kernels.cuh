@@ -988,9 +988,13 @@ struct GPCore {
 	static constexpr int J = 2 * NT;
 	static constexpr int NP = J * (J + 1) / 2;
 	double P[NP], g[J];
-	double quad, ldm, zmax, dmin;
+	double quad, ldm;
 	int lde;
-	bool notpd;
+	// max |z / D| and min D over the accumulated steps, tracked on the HIGH WORDS of the doubles (one integer
+	// max / min each instead of a compare and two selects per value): zhi bounds |z / D| from above to 2^-20,
+	// dhi bounds D from below; a non-positive D has a non-positive high word, which is how a matrix that is
+	// not positive definite is recognised at the end of the chunk (a NaN propagates through quad and log-det).
+	int zhi, dhi;
 };
 
 // One celerite step in carry form with prepared inputs: phi (per term), U, V (= cos, sin pairs),
@@ -1046,7 +1050,6 @@ __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], 
 	}
 	const double D = Avar - ut;
 	const double z = y - zp;
-	S.notpd |= !(D > 0.0);
 	const double invD = fast_rcp(D);
 	double vt[J], wv[J];
 #pragma unroll
@@ -1064,8 +1067,8 @@ __device__ __forceinline__ void gp_step(GPCore<NT> &S, const double (&phi)[NT], 
 	if (ACC) {
 		double zi = z * invD;
 		S.quad = fma(z, zi, S.quad);
-		S.zmax = fmax(S.zmax, fabs(zi));
-		S.dmin = fmin(S.dmin, D);
+		S.zhi = max(S.zhi, __double2hiint(zi) & 0x7fffffff);
+		S.dhi = min(S.dhi, __double2hiint(D));
 		// log-det as mantissa product + integer exponent
 		S.ldm *= D;
 		int hi = __double2hiint(S.ldm);
@@ -1114,7 +1117,6 @@ __device__ __forceinline__ void gp_step_scaled(GPCore<NT> &S, const double (&U)[
 	}
 	const double D = Avar - ut;
 	const double z = y - zp;
-	S.notpd |= !(D > 0.0);
 	const double invD = fast_rcp(D);
 	double vt[J], wv[J];
 #pragma unroll
@@ -1131,8 +1133,8 @@ __device__ __forceinline__ void gp_step_scaled(GPCore<NT> &S, const double (&U)[
 	if (ACC) {
 		double zi = z * invD;
 		S.quad = fma(z, zi, S.quad);
-		S.zmax = fmax(S.zmax, fabs(zi));
-		S.dmin = fmin(S.dmin, D);
+		S.zhi = max(S.zhi, __double2hiint(zi) & 0x7fffffff);
+		S.dhi = min(S.dhi, __double2hiint(D));
 		S.ldm *= D;
 		int hi = __double2hiint(S.ldm);
 		int ex = ((hi >> 20) & 0x7ff) - 1023;
@@ -1330,10 +1332,9 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	for (int i = 0; i < J; i++) S.g[i] = 0.0;
 	S.quad = 0.0;
 	S.ldm = 1.0;
-	S.zmax = 0.0;
-	S.dmin = CUDART_INF;
+	S.zhi = 0;
+	S.dhi = 0x7fefffff;
 	S.lde = 0;
-	S.notpd = false;
 	if (pass2 && active && c > 0) {
 		const double *cr = A.carryT + ((size_t)gw * A.nchunks + c) * CS;
 #pragma unroll
@@ -1373,23 +1374,22 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	// the row sit in registers, the next one requested 32 steps before its first use.
 	static_assert(TILE == 128, "the mask of one tile is four 32-bit words");
 	const uint4 *mrow = (TRANSIT && meanw) ? reinterpret_cast<const uint4 *>(A.winmask + (size_t)gw * A.nw32) : nullptr;
-	unsigned long long mlo = 0ull, mhi = 0ull;   // bits of the current tile's samples 0..63, 64..127
-	uint4 mnext = make_uint4(0u, 0u, 0u, 0u);    // the next tile's, in flight
+	uint4 mcur = make_uint4(0u, 0u, 0u, 0u);   // bits of the current tile's samples 0..31, 32..63, 64..95, 96..127
+	uint4 mnext = make_uint4(0u, 0u, 0u, 0u);  // the next tile's, in flight
 	auto mask_tile = [&](int tl, bool first) {   // at the start of tile tl (straight-line code: no branch in the step loop)
 		if (TRANSIT && meanw) {
-			const uint4 cur = first ? mrow[tl] : mnext;
+			mcur = first ? mrow[tl] : mnext;
 			mnext = mrow[min(tl + 1, A.nw32 / 4 - 1)];
-			mlo = ((unsigned long long)cur.y << 32) | cur.x;
-			mhi = ((unsigned long long)cur.w << 32) | cur.z;
 		}
 	};
 	const double4 *tile = nullptr;
 	auto load_mean = [&](int m) -> double {
 		double mv = 0.0;
 		if (TRANSIT && meanw) {
-			// always a load (the loop is scheduled around one): out of the window it reads a zero every lane shares
-			const unsigned long long q = (m & 64) ? mhi : mlo;
-			const double *src = ((q >> (m & 63)) & 1ull) ? meanw + m : A.zero;
+			// always a load (the loop is scheduled around one): out of the window it reads a zero every lane shares.
+			// m is uniform over the CTA, so the word selects run on uniform predicates.
+			const unsigned int wd = (m & 64) ? ((m & 32) ? mcur.w : mcur.z) : ((m & 32) ? mcur.y : mcur.x);
+			const double *src = ((wd >> (m & 31)) & 1u) ? meanw + m : A.zero;
 			mv = *src;
 		}
 		return mv;
@@ -1493,14 +1493,14 @@ GP_PRAGMA_UNROLL
 				const double mv3 = load_mean(min(a_ + 3, s1 - 1));
 				const double4 sm = tile[m];
 				const double ddt = sm.x - dt0_cur;
-				const double q0 = S.quad, l0 = S.ldm, z0 = S.zmax, d0 = S.dmin;
-				const int e0 = S.lde;
+				const double q0 = S.quad, l0 = S.ldm;
+				const int e0 = S.lde, z0 = S.zhi, d0 = S.dhi;
 				gp_step<NT, true>(S, phiC, UC, VC, yC, AC);
 				if (!acc) {
 					S.quad = q0;
 					S.ldm = l0;
-					S.zmax = z0;
-					S.dmin = d0;
+					S.zhi = z0;
+					S.dhi = d0;
 					S.lde = e0;
 				}
 				double UN[J], VN[J];
@@ -1610,9 +1610,9 @@ GP_PRAGMA_UNROLL
 		ChunkPartial pr;
 		pr.quad = S.quad;
 		pr.logdet = (double)S.lde * 0.693147180559945309417 + log(S.ldm);
-		pr.zmax = S.zmax;
-		pr.dmin = S.dmin;
-		if (S.notpd) {
+		pr.zmax = __hiloint2double(S.zhi, (int)0xffffffff);
+		pr.dmin = __hiloint2double(S.dhi, 0);
+		if (S.dhi <= 0) {
 			pr.logdet = CUDART_NAN;
 			atomicOr(&A.wstatus[gw], WF_NOTPD);
 		}

@@ -32,10 +32,9 @@ __global__ void __launch_bounds__(128, 2) single_kernel(const Walker *wk, const 
 	for (int i = 0; i < J; i++) S.g[i] = 0.0;
 	S.quad = 0.0;
 	S.ldm = 1.0;
-	S.zmax = 0.0;
-	S.dmin = 1e300;
+	S.zhi = 0;
+	S.dhi = 0x7fefffff;
 	S.lde = 0;
-	S.notpd = false;
 	double UC[J], VC[J];
 	for (int k = 0; k < NT; k++) {
 		UC[2 * k] = W.a[k];
