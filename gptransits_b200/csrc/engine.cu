@@ -474,7 +474,7 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	if (fuse_scan) {
 		// one thread per transit epoch: a few per 256 samples at most for any realistic period
 		int et = 32;
-		while (et < PREP_SCAN_THREADS && et * 256 < N) et *= 2;
+		while (et < PREP_SCAN_THREADS && et * GPT_SCAN_SAMPLES_PER_THREAD < N) et *= 2;
 		prep_threads = std::max(PREP_THREADS, et);
 	}
 	if (fuse_scan && !e->d_qfused.p) {

@@ -216,7 +216,13 @@ struct FinalAccept {
 // Sums are gathered in component / parameter order by one lane, so the arithmetic order does not
 // depend on the launch shape.
 constexpr int PREP_THREADS = 96;
-constexpr int PREP_SCAN_THREADS = 256;  // block size when the epoch scan rides on the prep kernel
+#ifndef GPT_PREP_SCAN_THREADS
+#define GPT_PREP_SCAN_THREADS 256
+#endif
+#ifndef GPT_SCAN_SAMPLES_PER_THREAD
+#define GPT_SCAN_SAMPLES_PER_THREAD 256
+#endif
+constexpr int PREP_SCAN_THREADS = GPT_PREP_SCAN_THREADS;  // block size when the epoch scan rides on the prep kernel
 
 // optional fused epoch scan (transit_epoch_scan_kernel's work for this walker, by the same CTA).  The
 // counter must be zero when the kernel starts: the finalize / diag kernel of the evaluation resets it.

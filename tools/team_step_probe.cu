@@ -196,6 +196,129 @@ __global__ void __launch_bounds__(128, 4) team_kernel(const Walker *wk, const do
 	}
 }
 
+// ---- lookahead form of the one-thread step: the product q = P U' with the matrix BEFORE the pending rank-one
+// update, corrected by the scalar sigma = (v . U') / D once D is known, so that the reciprocal's latency and the
+// matrix update are off the dependent chain (chain per step: sigma -> D -> 1/D).
+template <int DUMMY>
+__global__ void __launch_bounds__(128, 2) look_kernel(const Walker *wk, const double *y, int nsteps, double dt, double *out)
+{
+	constexpr int NP = J * (J + 1) / 2;
+	const int w = blockIdx.y * blockDim.x + threadIdx.x;
+	const Walker W = wk[w];
+	FastCoef<NT> K;
+	for (int k = 0; k < NT; k++) {
+		K.c[k] = W.c[k];
+		K.d[k] = W.d[k];
+	}
+	K.set_base(dt);
+	double P[NP], g[J];
+	for (int i = 0; i < NP; i++) P[i] = 0.0;
+	for (int i = 0; i < J; i++) g[i] = 0.0;
+	double quad = 0.0, ldm = 1.0;
+	int lde = 0;
+	__shared__ double s_y[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_y[i] = y[i];
+	__syncthreads();
+	const double Avar = W.asum + 2500.0;
+	double UC[J], VC[J];   // U~, V~ of the current step n
+	double q[J];           // P_{n-1} U_n
+	double vp[J], wp[J];   // v_{n-1}, w_{n-1}: the rank-one update still pending on P, g
+	double zp = 0.0, invDp = 0.0, cn = 0.0, kap = 0.0, zeta = 0.0;
+	auto prime = [&](int n) {
+		for (int k = 0; k < NT; k++) {
+			UC[2 * k] = W.a[k];
+			UC[2 * k + 1] = -W.b[k];
+			VC[2 * k] = 1.0;
+			VC[2 * k + 1] = 0.0;
+		}
+		double uq = 0.0, ug = 0.0;
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double a_ = 0.0;
+#pragma unroll
+			for (int j = 0; j < J; j++) a_ = fma((i <= j) ? P[tri(i, j, J)] : P[tri(j, i, J)], UC[j], a_);
+			q[i] = a_;
+			uq = fma(UC[i], a_, uq);
+			ug = fma(UC[i], g[i], ug);
+			vp[i] = wp[i] = 0.0;
+		}
+		kap = Avar - uq;
+		zeta = s_y[n & 255] - ug;
+		zp = 0.0;
+		invDp = 0.0;
+		cn = 0.0;
+	};
+	auto flush = [&]() {  // apply the pending update
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+#pragma unroll
+			for (int j = i; j < J; j++) P[tri(i, j, J)] = fma(vp[i], wp[j], P[tri(i, j, J)]);
+			g[i] = fma(wp[i], zp, g[i]);
+		}
+	};
+	const long long t0 = clock64();
+	for (int n = 0; n < nsteps; n++) {
+		if ((n & 63) == 0) {
+			if (n) {
+				flush();
+				double sc[NT];
+				for (int k = 0; k < NT; k++) sc[k] = exp(-W.c[k] * dt * 64);
+				for (int i = 0; i < J; i++) {
+					for (int j = i; j < J; j++) P[tri(i, j, J)] *= sc[i / 2] * sc[j / 2];
+					g[i] *= sc[i / 2];
+				}
+			}
+			prime(n);
+		}
+		// ---- dependent chain
+		const double sig = cn * invDp;
+		const double D = fma(-sig, cn, kap);
+		const double z = fma(-sig, zp, zeta);
+		double v[J];
+#pragma unroll
+		for (int i = 0; i < J; i++) v[i] = VC[i] - fma(vp[i], sig, q[i]);
+		const double invD = fast_rcp(D);
+		// ---- off the chain: pending update, next step's inputs and products
+		flush();
+		double UN[J], VN[J];
+		fast_advance<NT, 0>(K, 0.0, UC, VC, UN, VN);
+		double uq = 0.0, ug = 0.0, c1 = 0.0;
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			double a_ = 0.0;
+#pragma unroll
+			for (int j = 0; j < J; j++) a_ = fma((i <= j) ? P[tri(i, j, J)] : P[tri(j, i, J)], UN[j], a_);
+			q[i] = a_;
+			uq = fma(UN[i], a_, uq);
+			ug = fma(UN[i], g[i], ug);
+			c1 = fma(v[i], UN[i], c1);
+		}
+		kap = Avar - uq;
+		zeta = s_y[(n + 1) & 255] - ug;
+		cn = c1;
+#pragma unroll
+		for (int i = 0; i < J; i++) {
+			vp[i] = v[i];
+			wp[i] = v[i] * invD;
+			UC[i] = UN[i];
+			VC[i] = VN[i];
+		}
+		zp = z;
+		invDp = invD;
+		const double zi = z * invD;
+		quad = fma(z, zi, quad);
+		ldm *= D;
+		const int hi = __double2hiint(ldm);
+		const int ex = ((hi >> 20) & 0x7ff) - 1023;
+		lde += ex;
+		ldm = __hiloint2double(hi - (ex << 20), __double2loint(ldm));
+	}
+	const long long t1 = clock64();
+	out[3 * (blockIdx.x * gridDim.y * blockDim.x + w) + 0] = quad;
+	out[3 * (blockIdx.x * gridDim.y * blockDim.x + w) + 1] = (double)lde * 0.693147180559945309417 + log(ldm);
+	out[3 * (blockIdx.x * gridDim.y * blockDim.x + w) + 2] = (double)(t1 - t0);
+}
+
 int main(int argc, char **argv)
 {
 	const int nsteps = argc > 1 ? atoi(argv[1]) : 4096;
@@ -246,7 +369,18 @@ int main(int argc, char **argv)
 	};
 	for (int chunks : {148, 296}) time_it([&] { single_kernel<<<dim3(chunks, NW / 128), 128>>>(dw, dy, nsteps, dt, dout); }, "single", chunks, 1);
 	cudaMemcpy(o1.data(), dout, 8 * 3 * NW, cudaMemcpyDeviceToHost);
-	for (int chunks : {37, 74, 111, 148, 222})
+	std::vector<double> o3(3 * NW);
+	for (int chunks : {148, 296}) time_it([&] { look_kernel<0><<<dim3(chunks, NW / 128), 128>>>(dw, dy, nsteps, dt, dout); }, "look", chunks, 1);
+	cudaMemcpy(o3.data(), dout, 8 * 3 * NW, cudaMemcpyDeviceToHost);
+	{
+		double eq = 0, el = 0;
+		for (int w = 0; w < NW; w++) {
+			eq = fmax(eq, fabs(o1[3 * w] - o3[3 * w]) / fabs(o1[3 * w]));
+			el = fmax(el, fabs(o1[3 * w + 1] - o3[3 * w + 1]) / fabs(o1[3 * w + 1]));
+		}
+		printf("lookahead vs single: max rel diff quad %.2e logdet %.2e; clock64 per step %.0f\n", eq, el, o3[2] / nsteps);
+	}
+	for (int chunks : {37, 74})
 		time_it([&] { team_kernel<0><<<dim3(chunks, NW * TL / 128), 128>>>(dw, dy, nsteps, dt, dout); }, "team", chunks, TL);
 	cudaMemcpy(o2.data(), dout, 8 * 3 * NW, cudaMemcpyDeviceToHost);
 	double eq = 0, el = 0;
