@@ -100,6 +100,7 @@ SIGNATURES = {
     "gpt_sampler_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp, _dp]),
     "gpt_sampler_state": (C.c_int, [_vp, _dp, _dp, _i64p]),
     "gpt_sampler_rhat": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
+    "gpt_sampler_geweke": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, _i64p, C.c_double, C.c_double, _dp]),
     "gpt_sampler_end": (C.c_int, [_vp]),
     "gpt_sampler_reserve": (C.c_int, [_vp, C.c_int64]),
     "gpt_sampler_lq_device": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),

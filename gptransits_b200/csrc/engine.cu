@@ -1598,6 +1598,37 @@ int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat)
 	return GPT_OK;
 }
 
+int gpt_sampler_geweke(gpt_engine *e, int64_t first, int64_t count, int nbins, const int64_t *starts, double frac1,
+		       double frac2, double *z)
+{
+	if (!e || !z || !starts || !e->sampling || first < 0 || count < 2 || nbins < 1 || first + count > e->s_kept) {
+		if (e) e->set_error("sampler_geweke: range outside the kept steps");
+		return GPT_E_INVALID;
+	}
+	for (int b = 0; b < nbins; b++)
+		if (starts[b] < 0 || starts[b] >= count) {
+			e->set_error("sampler_geweke: a bin starts outside the range");
+			return GPT_E_INVALID;
+		}
+	cudaSetDevice(e->device);
+	const SamplerDev &S = e->S;
+	const size_t nz = (size_t)S.nstars * nbins * S.W * S.ndim;
+	DevBuf<double> out;
+	DevBuf<long long> st;
+	CK(out.ensure(nz));
+	CK(st.ensure(nbins));
+	static_assert(sizeof(long long) == sizeof(int64_t), "");
+	CK(cudaMemcpyAsync(st.p, starts, sizeof(int64_t) * nbins, cudaMemcpyHostToDevice, e->stream));
+	sampler_geweke_kernel<<<(unsigned)((nz + 127) / 128), 128, 0, e->stream>>>(S, first, count, nbins, st.p, frac1, frac2, out.p);
+	e->n_launch++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(z, out.p, sizeof(double) * nz, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	out.release();
+	st.release();
+	return GPT_OK;
+}
+
 // ---- single star, ensemble sharded by walker across ranks (one process per GPU) ------------------
 // Every rank holds the whole ensemble.  A half-step is: gpt_sampler_half_eval (proposals of all active
 // walkers; log-probabilities of this rank's slice [lo, hi) of them into lq) -> all-gather of lq by the

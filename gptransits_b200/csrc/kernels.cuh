@@ -2423,6 +2423,42 @@ __global__ void sampler_rhat_kernel(SamplerDev S, long long first, long long cou
 	}
 }
 
+// Geweke z-scores of the device-resident chain with the reference's conventions (convergence.py:75-99): for
+// every bin b the sub-chain [starts[b], count) is cut into its first frac1 and its last 1 - frac2 parts and
+// z = |mean_head - mean_tail| / sqrt(var_head + var_tail) (population variances) per walker and parameter.
+// One thread per (bin, walker, parameter); z [nstars][nbins][W][ndim].
+__global__ void sampler_geweke_kernel(SamplerDev S, long long first, long long count, int nbins, const long long *starts,
+				      double frac1, double frac2, double *z)
+{
+	const long long per_star = (long long)nbins * S.W * S.ndim;
+	const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= per_star * S.nstars) return;
+	const int star = (int)(id / per_star);
+	long long r = id - star * per_star;
+	const int b = (int)(r / ((long long)S.W * S.ndim));
+	r -= (long long)b * S.W * S.ndim;
+	const int w = (int)(r / S.ndim), d = (int)(r - (long long)w * S.ndim);
+	const long long s0 = starts[b], len = count - s0;
+	const long long k1 = (long long)(frac1 * (double)len), k2 = (long long)(frac2 * (double)len);  // int(frac * n)
+	const double *c = S.chain + (((size_t)star * S.W + w) * S.cap + first + s0) * S.ndim + d;
+	auto mean_var = [&](long long a, long long e_, double &m, double &v) {
+		const long long n = e_ - a;
+		double sum = 0.0;
+		for (long long i = a; i < e_; i++) sum += c[(size_t)i * S.ndim];
+		m = sum / (double)n;  // n == 0 -> NaN, as numpy's mean of an empty slice
+		double ss = 0.0;
+		for (long long i = a; i < e_; i++) {
+			const double t = c[(size_t)i * S.ndim] - m;
+			ss += t * t;
+		}
+		v = ss / (double)n;
+	};
+	double mh, vh, mt, vt;
+	mean_var(0, k1, mh, vh);
+	mean_var(k2, len, mt, vt);
+	z[id] = fabs((mh - mt) / sqrt(vh + vt));
+}
+
 // ================================================================== FP64 peak probe
 __global__ void dfma_peak_kernel(double *out, int iters)
 {

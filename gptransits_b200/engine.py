@@ -192,6 +192,15 @@ class Engine:
         self._ck(self._lib.gpt_sampler_rhat(self._h, int(first), int(count), _p(out)))
         return out
 
+    def sampler_geweke(self, first, count, frac1=0.1, frac2=0.5, bins=10):
+        """Geweke z-scores (convergence.geweke's conventions) of kept steps [first, first+count) on the device:
+        -> starts[bins], z[nstars, bins, W, ndim]."""
+        starts = np.ascontiguousarray(np.linspace(0, int(count) / 2, num=bins).astype(np.int64))
+        z = np.empty((self._sns, bins, self._sW, self.ndim))
+        self._ck(self._lib.gpt_sampler_geweke(self._h, int(first), int(count), int(bins),
+                                              starts.ctypes.data_as(C.POINTER(C.c_int64)), float(frac1), float(frac2), _p(z)))
+        return starts, z
+
     def sampler_end(self):
         self._ck(self._lib.gpt_sampler_end(self._h))
 

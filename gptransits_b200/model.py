@@ -205,6 +205,7 @@ class Model:
         block = max(1, min(block, remaining))
         chains, logps = ([chain0] if chain0 is not None else []), ([logp0] if logp0 is not None else [])
         self.block_rhat = []
+        self.block_geweke = []
         eng.sampler_begin(init, seed=self.settings["seed"], step0=done)
         try:
             while remaining > 0:
@@ -221,6 +222,12 @@ class Model:
                     rhat = eng.sampler_rhat(0, n)[0]
                     self.block_rhat.append(rhat)
                     log.info(f"iteration {done}: max Gelman-Rubin V/W over the last {n} steps = {rhat.max():.4f}")
+                    if n >= 40:
+                        # Geweke z-scores of the block (the burn-in criterion of model.py:387-402), also on the device
+                        _, zs = eng.sampler_geweke(0, n)
+                        frac = float(np.mean(np.nanmax(zs[0][0], axis=1) > 2))
+                        self.block_geweke.append(frac)
+                        log.info(f"iteration {done}: {100 * frac:.0f}% of the walkers have a Geweke z-score above 2 in this block")
                     stop = self.settings.get("rhat_stop")
                     if stop and rhat.max() < stop:
                         log.info(f"stopping early: V/W below {stop}")

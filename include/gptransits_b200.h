@@ -173,6 +173,12 @@ int gpt_sampler_state(gpt_engine *e, double *coords, double *logp, int64_t *nacc
  * kept steps [first, first + count) of the device chain, per star and parameter: rhat[nstars*ndim].
  * Replaces pulling the chain to the host for the check at model.py:417-424 while a run is in flight. */
 int gpt_sampler_rhat(gpt_engine *e, int64_t first, int64_t count, double *rhat);
+/* Geweke z-scores (convergence.py:75-99, used for the burn-in at model.py:387-402) of the kept steps
+ * [first, first + count) of the device chain: for bin b the sub-chain from starts[b] (relative to first; the
+ * reference's np.linspace(0, count/2, nbins).astype(int)) is cut into its first frac1 and its part after frac2,
+ * z = |mean_head - mean_tail| / sqrt(var_head + var_tail).  z [nstars][nbins][W][ndim]. */
+int gpt_sampler_geweke(gpt_engine *e, int64_t first, int64_t count, int nbins, const int64_t *starts, double frac1,
+		       double frac2, double *z);
 /* One star on several GPUs (one process each): the ensemble is sharded by walker.  Every rank
  * holds the whole ensemble; per half-step: gpt_sampler_half_eval proposes for all active walkers and
  * evaluates this rank's slice [lo, hi) of them into the device array lq[W/2] (gpt_sampler_lq_device), the

@@ -226,3 +226,30 @@ def test_batch_upload_on_one_grid_equals_star_by_star(engine):
         assert np.array_equal(got3, engine.log_prob(theta[3:4], star=0, nstars=1))
     finally:
         engine.set_option("chunks", 0)
+
+
+def test_device_geweke_matches_the_host_definition(engine, kic_lc, kic_config):
+    """gpt_sampler_geweke on the device-resident chain == convergence.geweke (the reference's definition,
+    convergence.py:75-99) on the same chain pulled to the host."""
+    from gptransits_b200.convergence import geweke
+    t, f, e = kic_lc
+    gp = GPModel(kic_config["gp"])
+    spec = build_spec(gp, None)
+    np.random.seed(6)
+    init = gp.sample_prior(24)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_star(0, t, (f - 1) * 1e6, e * 1e6)
+    engine.sampler_begin(init, seed=4)
+    try:
+        engine.sampler_run(120, keep=True)
+        chain, _ = engine.sampler_read(0, 120)
+        for first, count, bins in ((0, 120, 10), (17, 90, 7)):
+            starts, z = engine.sampler_geweke(first, count, bins=bins)
+            hs, hz = geweke(chain[0][:, first:first + count, :], bins=bins)
+            assert np.array_equal(starts, hs)
+            ok = np.isfinite(hz)
+            assert np.array_equal(np.isfinite(z[0]), ok)
+            assert np.max(np.abs(z[0][ok] - hz[ok]) / np.maximum(np.abs(hz[ok]), 1e-300)) < 1e-9
+    finally:
+        engine.sampler_end()
