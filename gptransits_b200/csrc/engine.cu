@@ -497,8 +497,11 @@ static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_th
 	sc.qcount = qcount;
 	sc.winmask = fuse_scan ? winmask : nullptr;  // cleared by whichever kernel runs the scan
 	sc.nw32 = nw32;
-	if (nwalk <= 4096)
-		launch_k(prep_kernel, dim3(nwalk), dim3(prep_threads), fuse_scan ? scan_smem_bytes(N) : 0, st, m, dst, W, d_theta, nwalk,
+	if (nwalk <= 4096 && fuse_scan)
+		launch_k(prep_kernel<true>, dim3(nwalk), dim3(prep_threads), scan_smem_bytes(N), st, m, dst, W, d_theta, nwalk,
+			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
+	else if (nwalk <= 4096)
+		launch_k(prep_kernel<false>, dim3(nwalk), dim3(PREP_THREADS), 0, st, m, dst, W, d_theta, nwalk,
 			 e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	else
 		launch_k(prep_wide_kernel, dim3((nwalk + 63) / 64), dim3(64), 0, st, m, dst, W, d_theta, nwalk, e->d_prep.p, e->d_flags.p, reset, pr);
@@ -1954,7 +1957,7 @@ int gpt_gp_predict(gpt_engine *e, int star, const double *theta, const double *x
 		memset(&pr, 0, sizeof(pr));
 		PrepScan sc;
 		memset(&sc, 0, sizeof(sc));
-		launch_k(prep_kernel, dim3(1), dim3(PREP_THREADS), 0, st, m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr, sc);
+		launch_k(prep_kernel<false>, dim3(1), dim3(PREP_THREADS), 0, st, m, dst, 1, e->d_theta.p, 1, e->d_prep.p, e->d_flags.p, reset, pr, sc);
 	}
 	if (m.has_transit) {
 		dim3 g(1, (N + TR_THREADS - 1) / TR_THREADS);

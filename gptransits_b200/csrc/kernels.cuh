@@ -237,7 +237,10 @@ struct PrepScan {
 __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, unsigned long long *queue,
 				  unsigned int *qcount, int items_cap);
 
-__global__ void __launch_bounds__(PREP_SCAN_THREADS)
+// SCAN: the walker's epoch scan rides on the kernel (small batches); the scan-free instantiation needs half the
+// registers, so that batches of thousands of walkers (one CTA each) run in fewer waves.
+template <bool SCAN>
+__global__ void __launch_bounds__(SCAN ? PREP_SCAN_THREADS : PREP_THREADS, SCAN ? 1 : 16)
 prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nwalk, double *prep, int *flags,
 	    PrepReset R, PrepPropose PR, PrepScan SC)
 {
@@ -390,7 +393,7 @@ prep_kernel(ModelDev m, const StarDev *stars, int W, const double *theta, int nw
 		if (m.has_transit && pp[PP_WHALF] >= 0.5) fl |= WF_TR_ALL;
 		flags[gw] = fl;
 	}
-	if (SC.enabled) {
+	if (SCAN && SC.enabled) {
 		// the walker's window is complete (written by this CTA): queue its in-window samples right away
 		__syncthreads();
 		if (flags[gw] & WF_VALID) epoch_scan_walker(st, gw, pp, SC.queue, SC.qcount, SC.items_cap);
@@ -1762,14 +1765,21 @@ __global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_
 	// all written by the prep kernel or earlier
 	const bool acc_warp = A.AC.enabled && (WARP || (tid >> 5) == FIN_THREADS / 32 - 1);
 	AcceptPre pre;
+	if (A.skip_if_clean) {
+		// second invocation (after the repair pass): nothing to do unless this walker was flagged
+		pdl_wait();
+		pdl_trigger();
+		if (*A.nbad == 0 || !A.wbad[gw]) return;
+	}
 	if (acc_warp) sampler_accept_prefetch(A.AC.S, A.AC.step, A.AC.half, gw, lane, pre);
-	pdl_wait();
-	pdl_trigger();
+	if (!A.skip_if_clean) {
+		pdl_wait();
+		pdl_trigger();
+	}
 	if (gw == 0 && tid == 0 && A.qreset && !A.skip_if_clean) {
 		A.qreset[1] = A.qreset[0];
 		A.qreset[0] = 0;
 	}
-	if (A.skip_if_clean && (*A.nbad == 0 || !A.wbad[gw])) return;  // second invocation: flagged walkers only
 	constexpr int GS_ = G;  // stride of the walker's threads over chunks
 	const int fl = A.flags[gw];
 	const double *pp = A.prep + (size_t)gw * PREP_STRIDE;
@@ -1887,8 +1897,11 @@ __global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_
 				atomicAdd(A.nbad, nbad);
 				atomicAdd(A.acc, (unsigned long long)nbad);
 			}
-			atomicMax((unsigned long long *)A.verr, (unsigned long long)__double_as_longlong(worst));
-			atomicMax(A.acc + 1, (unsigned long long)__double_as_longlong(worst));
+			// (a maximum: skip the atomic when the stored value already covers this walker's -- thousands of
+			// walkers would otherwise serialise on the two addresses)
+			const unsigned long long wb = (unsigned long long)__double_as_longlong(worst);
+			if (wb > *(volatile unsigned long long *)A.verr) atomicMax((unsigned long long *)A.verr, wb);
+			if (wb > *(volatile unsigned long long *)(A.acc + 1)) atomicMax(A.acc + 1, wb);
 		}
 		walker_bad = group_or(nbad > 0) ? 1 : 0;
 		if (walker_bad) {

@@ -253,3 +253,44 @@ def test_device_geweke_matches_the_host_definition(engine, kic_lc, kic_config):
             assert np.max(np.abs(z[0][ok] - hz[ok]) / np.maximum(np.abs(hz[ok]), 1e-300)) < 1e-9
     finally:
         engine.sampler_end()
+
+
+def test_large_batch_cut_into_a_few_chunks(engine):
+    """Thousands of walkers cut into a few chunks (what one rank of the C4 batch runs on 4 or 8 GPUs) go through
+    the warp-per-walker finalize: parity with the oracle with a sufficient halo, with a useless one (every
+    boundary flagged, chunk-by-chunk repair and whole-walker recomputation), and through the sampler."""
+    from gptransits_b200 import synth
+    np.random.seed(21)
+    gp = GPModel(synth.c3_config()["gp"])
+    spec = build_spec(gp, None)
+    ns, W, N = 32, 32, 2048
+    t, y, yerr, th = synth.make_stars(ns, N, seed0=91)
+    theta = gp.sample_prior(ns * W).reshape(ns, W, -1)
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.upload_stars(0, t, y, yerr)
+    check = (0, 13, 31)
+    want = {s: oracle.log_prob(spec, t, y[s], yerr, theta[s], return_parts=True)[1] for s in check}
+    try:
+        for chunks, halo, flagged in ((4, 448, False), (4, 4, True), (2, 0, False)):
+            engine.set_option("chunks", chunks)
+            engine.set_option("halo", halo)
+            before = engine.stat("pass2_chunks")
+            _, parts = engine.log_prob(theta, star=0, nstars=ns, return_parts=True)
+            assert engine.stat("chunks") == chunks
+            if flagged:
+                assert engine.stat("pass2_chunks") > before
+            for s in check:
+                assert_parts_close(parts[s], want[s])
+        # the sampler's fused accept on the same finalize kernel, with the repair launches in line
+        engine.set_option("chunks", 4)
+        engine.set_option("halo", 4)
+        engine.set_option("speculate", 0)
+        chain, logp, nacc = engine.sample(theta, 3, seed=17, nstars=ns)
+        for s in check:
+            ochain, ologp, onacc = oracle.sample(spec, t, y[s], yerr, theta[s], 3, seed=17, star=s)
+            assert np.array_equal(nacc[s], onacc) and rel(chain[s], ochain) < 1e-9
+    finally:
+        engine.set_option("speculate", 1)
+        engine.set_option("chunks", 0)
+        engine.set_option("halo", 0)
