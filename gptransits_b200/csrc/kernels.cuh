@@ -1736,12 +1736,36 @@ __device__ __forceinline__ void sampler_accept_commit(const SamplerDev &S, const
 	}
 }
 
+// weighted sizes of a boundary's carry and of the difference between its two versions (state matrix, forward vector)
+template <int J>
+__device__ __forceinline__ void carry_errors(const double *ct, const double *ce, const double (&ua)[J], double &eS, double &nS,
+					     double &ef, double &nf)
+{
+	constexpr int NP = J * (J + 1) / 2;
+	eS = ef = nS = nf = 0.0;
+#pragma unroll
+	for (int i = 0; i < J; i++)
+#pragma unroll
+		for (int j = i; j < J; j++) {
+			const double wgt = (i == j ? 1.0 : 2.0) * ua[i] * ua[j];
+			const double c = ct[tri(i, j, J)];
+			eS += wgt * fabs(c - ce[tri(i, j, J)]);
+			nS += wgt * fabs(c);
+		}
+#pragma unroll
+	for (int i = 0; i < J; i++) {
+		const double c = ct[NP + i];
+		ef += ua[i] * fabs(c - ce[NP + i]);
+		nf += ua[i] * fabs(c);
+	}
+}
+
 // G threads per walker: FIN_THREADS (one block per walker: light curves cut into many chunks, few walkers) or 32
 // (one warp per walker, FINW_WALKERS walkers per block: batches of thousands of walkers cut into a few chunks,
 // where a block per walker costs more in scheduling than the work it does).
 constexpr int FINW_WALKERS = 8;
 template <int NT, int G>
-__global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_finalize_kernel(FinalArgs A)
+__global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS, G == 32 ? 3 : 1) gp_finalize_kernel(FinalArgs A)
 {
 	constexpr int J = 2 * NT, NP = J * (J + 1) / 2, CS = NP + J;
 	constexpr bool WARP = G == 32;
@@ -1818,7 +1842,9 @@ __global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_
 	pr0.quad = pr0.logdet = pr0.zmax = 0.0;
 	pr0.dmin = 1.0;
 	const int k0 = 1 + tid;
-	if (do_verify && k0 < A.nchunks) {
+	// (one warp per walker: thousands of walkers, a few boundaries each -- the carries are streamed from memory
+	// inside the loop instead, which keeps the kernel at a third of the registers and three times the resident warps)
+	if (!WARP && do_verify && k0 < A.nchunks) {
 		const double *ct = A.carryT + ((size_t)gw * A.nchunks + k0) * CS;
 		const double *ce = A.carryE + ((size_t)gw * A.nchunks + k0) * CS;
 #pragma unroll
@@ -1844,29 +1870,14 @@ __global__ void __launch_bounds__(G == 32 ? 32 * FINW_WALKERS : FIN_THREADS) gp_
 		double worst = 0.0;
 		int nbad = 0;
 		for (int k = k0; k < A.nchunks; k += GS_) {
-			if (k != k0) {
+			double eS, ef, nS, nf;
+			if (WARP || k != k0) {
 				const double *ct = A.carryT + ((size_t)gw * A.nchunks + k) * CS;
 				const double *ce = A.carryE + ((size_t)gw * A.nchunks + k) * CS;
-#pragma unroll
-				for (int i = 0; i < CS; i++) {
-					ct0[i] = ct[i];
-					ce0[i] = ce[i];
-				}
 				pr0 = A.partial[(size_t)gw * A.nchunks + k];
-			}
-			double eS = 0.0, ef = 0.0, nS = 0.0, nf = 0.0;
-#pragma unroll
-			for (int i = 0; i < J; i++)
-#pragma unroll
-				for (int j = i; j < J; j++) {
-					const double wgt = (i == j ? 1.0 : 2.0) * ua[i] * ua[j];
-					eS += wgt * fabs(ct0[tri(i, j, J)] - ce0[tri(i, j, J)]);
-					nS += wgt * fabs(ct0[tri(i, j, J)]);
-				}
-#pragma unroll
-			for (int i = 0; i < J; i++) {
-				ef += ua[i] * fabs(ct0[NP + i] - ce0[NP + i]);
-				nf += ua[i] * fabs(ct0[NP + i]);
+				carry_errors<J>(ct, ce, ua, eS, nS, ef, nf);
+			} else {
+				carry_errors<J>(ct0, ce0, ua, eS, nS, ef, nf);
 			}
 			// The halo started from a zero carry, i.e. from an error as large as the state itself, and
 			// left eS (ef) of it after H steps: a geometric decay whose remaining sum over the chunk is
