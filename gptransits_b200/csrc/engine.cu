@@ -99,6 +99,7 @@ struct gpt_engine {
 	long long spec_need_steps = 128;  // clean record needed before a block runs speculatively; doubles on a replay
 	bool spec_last_clean = true;
 	long long n_spec_replays = 0;
+	int opt_scratch_cap_mb = 8192;  // most scratch (transit model + queue) one evaluation may hold; larger batches are sliced
 	int opt_async_egress = 1;  // gpt_sample: the chain leaves for the host range by range while the sampler runs
 	long long n_egress_jobs = 0;
 	double opt_tol = 5e-10;   // budget (a bound, not an estimate) for the chunk-coupling error, relative to quad and to logdet
@@ -430,9 +431,54 @@ static void launch_chunk(int nt, bool transit, dim3 grid, int threads, cudaStrea
 // Enqueue one posterior evaluation of nstars*W walkers.  theta/lp/parts are device pointers.
 // host_sync: read the verification verdict back and launch pass 2 only when needed; otherwise pass 2
 // is always enqueued (it exits immediately when nothing was flagged) so the sequence is graph-safe.
+static int eval_enqueue_batch(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
+			      double *d_parts, bool host_sync, const PrepPropose *propose, const FinalAccept *accept,
+			      bool *accept_done, bool speculative);
+
+// One posterior evaluation of nstars x W walkers.  The transit model and its work queue are scratch of
+// 16 bytes per (walker, sample); a plain evaluation (no fused proposal / accept) whose scratch would exceed
+// "scratch_cap_mb" is run as a sequence of sub-batches -- whole stars, or slices of the walkers of one star --
+// that reuse the same scratch, so the footprint is bounded by the cap, not by nwalk x N.
 static int eval_enqueue(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
 			double *d_parts, bool host_sync, const PrepPropose *propose = nullptr,
 			const FinalAccept *accept = nullptr, bool *accept_done = nullptr, bool speculative = false)
+{
+	if (!propose && !accept && e->have_model && e->model.has_transit && star0 >= 0 && nstars >= 1 &&
+	    (size_t)(star0 + nstars) <= e->stars.size() && e->stars[star0].N > 0) {
+		const double per_walker = 16.0 * (double)e->stars[star0].N;
+		const double cap = (double)e->opt_scratch_cap_mb * 1048576.0;
+		if (per_walker * (double)nstars * (double)W > cap) {
+			const int ndim = e->model.ndim;
+			const long long fit = std::max<long long>(32, (long long)(cap / per_walker));  // walkers per sub-batch
+			if (fit >= W) {
+				const int sper = (int)std::max<long long>(1, fit / W);  // whole stars
+				for (int s0 = 0; s0 < nstars; s0 += sper) {
+					const int sn = std::min(sper, nstars - s0);
+					int rc = eval_enqueue_batch(e, star0 + s0, sn, d_theta + (size_t)s0 * W * ndim, W, d_lp + (size_t)s0 * W,
+								    d_parts ? d_parts + (size_t)s0 * W * 4 : nullptr, host_sync, nullptr, nullptr,
+								    nullptr, speculative);
+					if (rc) return rc;
+				}
+			} else {
+				for (int s = 0; s < nstars; s++)
+					for (int w0 = 0; w0 < W; w0 += (int)fit) {
+						const int wn = (int)std::min<long long>(fit, W - w0);
+						const size_t off = (size_t)s * W + w0;
+						int rc = eval_enqueue_batch(e, star0 + s, 1, d_theta + off * ndim, wn, d_lp + off,
+									    d_parts ? d_parts + off * 4 : nullptr, host_sync, nullptr, nullptr, nullptr,
+									    speculative);
+						if (rc) return rc;
+					}
+			}
+			return GPT_OK;
+		}
+	}
+	return eval_enqueue_batch(e, star0, nstars, d_theta, W, d_lp, d_parts, host_sync, propose, accept, accept_done, speculative);
+}
+
+static int eval_enqueue_batch(gpt_engine *e, int star0, int nstars, const double *d_theta, int W, double *d_lp,
+			      double *d_parts, bool host_sync, const PrepPropose *propose, const FinalAccept *accept,
+			      bool *accept_done, bool speculative)
 {
 	if (accept_done) *accept_done = false;
 	int rc = check_stars(e, star0, nstars);
@@ -730,6 +776,8 @@ int gpt_set_option(gpt_engine *e, const char *key, double value)
 	} else if (k == "speculate") {
 		e->opt_speculate = std::min(2, std::max(0, (int)value));
 		e->spec_last_clean = true;
+	} else if (k == "scratch_cap_mb") {
+		e->opt_scratch_cap_mb = std::max(1, (int)value);
 	} else if (k == "async_egress") {
 		e->opt_async_egress = value != 0;
 	} else if (k == "pdl") {

@@ -88,7 +88,8 @@ const char *gpt_version(void);
  * "fuse_scan" (epoch scan inside the prep kernel for small batches, default 1), "transit_strict" (batman's
  * operation order), "series_order_min" (0..4: lowest treatment of regular-cadence steps, 4 = general loop),
  * "pdl" (programmatic dependent launch, default 0), "speculate" (sampler blocks without repair launches,
- * replayed when a chunk was flagged: 0 never, 1 after a long clean record -- default --, 2 eagerly), "async_egress"
+ * replayed when a chunk was flagged: 0 never, 1 after a long clean record -- default --, 2 eagerly), "scratch_cap_mb" (default 8192: an evaluation
+ * whose transit-model scratch, 16 bytes per walker and sample, would exceed it runs as sub-batches), "async_egress"
  * (gpt_sample streams finished step ranges of the chain to the host while sampling, default 1), "time_kernels", "reset_timers".
  * Counters: "launches", "evals", "pass2_chunks", "spec_replays", "verify_ratio", "halo", "chunks", "chunk_len",
  * "transit_items", "ms_<kernel>" / "n_<kernel>" for prep, transit, trscan, chunk, final, pass2. */

@@ -294,3 +294,38 @@ def test_large_batch_cut_into_a_few_chunks(engine):
         engine.set_option("speculate", 1)
         engine.set_option("chunks", 0)
         engine.set_option("halo", 0)
+
+
+def test_scratch_cap_slices_large_evaluations(engine, sim_lc, sim_config):
+    """An evaluation whose transit-model scratch (16 bytes per walker and sample) exceeds "scratch_cap_mb" runs as
+    sub-batches -- whole stars, or slices of one star's walkers -- with the same results."""
+    from test_gpu_parity import sim_setup
+    t, y, yerr, spec, gp, tr = sim_setup(sim_lc, sim_config, "cosi")
+    np.random.seed(12)
+    W, ns = 96, 3
+    theta = np.hstack([gp.sample_prior(W * ns), tr.sample_prior(W * ns)]).reshape(ns, W, -1)
+    theta[..., 9] = np.random.uniform(5, 15, (ns, W))
+    theta[..., 10] = np.random.uniform(0, 0.05, (ns, W))
+    engine.clear_stars()
+    engine.set_model(spec)
+    for s in range(ns):
+        engine.upload_star(s, t, y + 3.0 * s, yerr)
+    try:
+        engine.set_option("chunks", 1)
+        want, wparts = engine.log_prob(theta, star=0, nstars=ns, return_parts=True)
+        assert np.isfinite(want).sum() > ns * W // 2
+        per_walker_mb = 16.0 * t.size / 2**20
+        launches = engine.stat("launches")
+        full = None
+        for cap_walkers in (2 * W, 40):       # whole stars per sub-batch; slices of a star's walkers
+            engine.set_option("scratch_cap_mb", max(1, int(per_walker_mb * cap_walkers)))
+            before = engine.stat("launches")
+            got, parts = engine.log_prob(theta, star=0, nstars=ns, return_parts=True)
+            if full is None:
+                full = before - launches
+            assert engine.stat("launches") - before > full     # more than one sub-batch ran
+            assert np.array_equal(np.isfinite(got), np.isfinite(want))
+            assert_parts_close(parts, wparts, rtol=1e-12)
+    finally:
+        engine.set_option("scratch_cap_mb", 8192)
+        engine.set_option("chunks", 0)
