@@ -214,6 +214,16 @@ class Engine:
         self._ck(self._lib.gpt_sampler_lq_device(self._h, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
+    def device_copy(self, host, device_ptr, to_device):
+        """Copy between a contiguous float64 host array and device memory of this engine (engine stream, synchronous)."""
+        host = np.ascontiguousarray(host, dtype=np.float64) if to_device else host
+        if host.nbytes:
+            if to_device:
+                self._ck(self._lib.gpt_device_copy(self._h, C.c_void_p(int(device_ptr)), host.ctypes.data_as(C.c_void_p), host.nbytes, 1))
+            else:
+                self._ck(self._lib.gpt_device_copy(self._h, host.ctypes.data_as(C.c_void_p), C.c_void_p(int(device_ptr)), host.nbytes, 0))
+        return host
+
     def sampler_half_eval(self, half, lo, hi):
         self._ck(self._lib.gpt_sampler_half_eval(self._h, int(half), int(lo), int(hi)))
 

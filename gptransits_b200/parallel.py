@@ -77,17 +77,26 @@ def run_walker_sharded(engine, dist, init, nsteps, seed=42, step0=0, a=2.0, time
             ms = engine.sampler_run_sharded(nsteps, keep=True, timed=timed)
             chain, logp = engine.sampler_read(0, nsteps)
             return (chain[0], logp[0], ms) if timed else (chain[0], logp[0])
+        staged = world > 1 and dist.get_backend() != "nccl"   # no device collective: the slices travel through the host
         if world > 1:
             import torch
             ptr, count = engine.sampler_lq_device()
-            lq = torch.as_tensor(_DeviceArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+            if not staged:
+                lq = torch.as_tensor(_DeviceArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
         slices = [walker_slice(H, r, world) for r in range(world)]
         lo, hi = slices[rank]
         even = H % world == 0
         for _ in range(nsteps):
             for half in (0, 1):
                 engine.sampler_half_eval(half, lo, hi)          # returns with the engine's stream drained
-                if world > 1:
+                if staged:
+                    mine = np.empty(hi - lo)
+                    if hi > lo:
+                        engine.device_copy(mine, ptr + 8 * lo, to_device=False)
+                    parts = [None] * world
+                    dist.all_gather_object(parts, mine)
+                    engine.device_copy(np.ascontiguousarray(np.concatenate(parts)), ptr, to_device=True)
+                elif world > 1:
                     if even:
                         dist.all_gather_into_tensor(lq, lq[lo:hi].clone())
                     else:

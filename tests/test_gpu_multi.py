@@ -110,3 +110,39 @@ def test_two_gpu_sharding(tmp_path):
         eng.sampler_end()
         assert np.array_equal(c[0], got[s])
     eng.close()
+
+
+def _worker_one_gpu(rank, world, port, outdir):
+    """Two ranks on ONE GPU: the half-step C ABI (gpt_sampler_half_eval / half_accept) with the slices of the
+    proposal log-probabilities exchanged through the host (gloo) -- the walker-sharded protocol on a box where
+    NCCL cannot run (it refuses two ranks on one device)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, y, yerr, spec, init = _setup()
+    from gptransits_b200 import Engine
+    from gptransits_b200.parallel import run_walker_sharded
+    eng = Engine(0)
+    eng.set_model(spec)
+    eng.upload_star(0, t, y, yerr)
+    chain, logp = run_walker_sharded(eng, dist, init, 6, seed=9)
+    np.save(Path(outdir) / f"gwalker_{rank}.npy", chain)
+    dist.barrier()
+    dist.destroy_process_group()
+    eng.close()
+
+
+@pytest.mark.skipif(_ngpu() < 1, reason="needs a GPU")
+def test_walker_sharding_two_ranks_on_one_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_one_gpu, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    t, y, yerr, spec, init = _setup()
+    from gptransits_b200 import Engine
+    eng = Engine(0)
+    eng.set_model(spec)
+    eng.upload_star(0, t, y, yerr)
+    want, _, _ = eng.sample(init, 6, seed=9)
+    eng.close()
+    g0, g1 = np.load(tmp_path / "gwalker_0.npy"), np.load(tmp_path / "gwalker_1.npy")
+    assert np.array_equal(g0, g1)
+    assert np.max(np.abs(g0 - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
