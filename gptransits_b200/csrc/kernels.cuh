@@ -704,6 +704,11 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 					a = lower_bound(lo);
 					int b = lower_bound(hi);        // first t >= hi ...
 					while (b < N && t[b] <= hi) b++;  // ... then past the samples equal to hi
+					// The window is an interval of time and the times are sorted, so only the ends of the
+					// (slightly widened) bracket can fail the per-sample test: trim them with the test itself and
+					// every sample in between is in the window -- no load, no test for the bulk of a long window.
+					while (a < b && !in_transit_window(t[a], wcen, inv_per, whalf)) a++;
+					while (b > a && !in_transit_window(t[b - 1], wcen, inv_per, whalf)) b--;
 					cnt = max(b - a, 0);
 				}
 			}
@@ -720,39 +725,18 @@ __device__ void epoch_scan_walker(const StarDev &st, int gw, const double *pp, u
 			}
 			const int total = s_off[nthr];
 			__syncthreads();  // every thread has read the total before the next round's scan overwrites s_off
-			for (int f0 = 0; f0 < total; f0 += items_cap) {
-				const int f1 = min(total, f0 + items_cap);
-				if (tid == 0) s_n = 0;
+			// (the brackets were trimmed to in-window samples: the items go straight to the global queue, one
+			// atomic per round of epochs)
+			if (total > 0) {
+				if (tid == 0) s_base = atomicAdd(qcount, (unsigned int)total);
 				__syncthreads();
-				for (int fb = f0; fb < f1; fb += nthr) {
-					const int f = fb + tid;
-					bool inw = false;
-					int n = 0;
-					if (f < f1) {
-						int ea = 0, eb = nthr;  // last epoch e with s_off[e] <= f
-						while (eb - ea > 1) {
-							const int md = (ea + eb) >> 1;
-							if (s_off[md] <= f) ea = md; else eb = md;
-						}
-						n = s_a[ea] + (f - s_off[ea]);
-						inw = in_transit_window(t[n], wcen, inv_per, whalf);
+				for (int f = tid; f < total; f += nthr) {
+					int ea = 0, eb = nthr;  // last epoch e with s_off[e] <= f
+					while (eb - ea > 1) {
+						const int md = (ea + eb) >> 1;
+						if (s_off[md] <= f) ea = md; else eb = md;
 					}
-					const unsigned mask = __ballot_sync(0xffffffffu, inw);
-					if (mask) {
-						const int lane = tid & 31, leader = __ffs(mask) - 1;
-						unsigned int base = 0;
-						if (lane == leader) base = atomicAdd(&s_n, (unsigned int)__popc(mask));
-						base = __shfl_sync(0xffffffffu, base, leader);
-						if (inw) s_items[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)n;
-					}
-				}
-				__syncthreads();
-				const unsigned int have = s_n;
-				if (have) {
-					if (tid == 0) s_base = atomicAdd(qcount, have);
-					__syncthreads();
-					for (unsigned int i = tid; i < have; i += nthr)
-						queue[s_base + i] = ((unsigned long long)(unsigned)gw << 32) | s_items[i];
+					queue[s_base + (unsigned int)f] = ((unsigned long long)(unsigned)gw << 32) | (unsigned int)(s_a[ea] + (f - s_off[ea]));
 				}
 				__syncthreads();
 			}
