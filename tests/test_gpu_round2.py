@@ -329,3 +329,46 @@ def test_scratch_cap_slices_large_evaluations(engine, sim_lc, sim_config):
     finally:
         engine.set_option("scratch_cap_mb", 8192)
         engine.set_option("chunks", 0)
+
+
+def test_transit_mask_on_edge_shapes(engine):
+    """GP + transit on light curves whose length is not a multiple of the 32-bit mask words or of the 128-sample
+    tiles, with short periods (several windows per tile), a walker that is in transit everywhere (a/R* ~ 1.6: the
+    window covers the whole orbit) and a NaN transit parameter; one chunk and forced chunks with a halo."""
+    import copy
+    cfg_tr = copy.deepcopy(C3_CONFIG_TR)
+    v = cfg_tr["params"]["values"]
+    v["P"] = [False, None, "uniform", 0.2, 9.0]
+    v["t0"] = [False, None, "uniform", 0.0, 5.0]
+    v["Rrat"] = [False, None, "uniform", 0.01, 0.2]
+    v["aR"] = [False, None, "uniform", 1.2, 15.0]
+    v["cosi"] = [False, None, "uniform", 70.0, 90.0]
+    gp = GPModel(C3_CONFIG_GP)
+    try:
+        for N, chunks, halo in ((1, 0, 0), (2, 0, 0), (31, 0, 0), (33, 0, 0), (127, 0, 0), (129, 0, 0), (257, 0, 0),
+                                (1000, 1, 0), (1000, 5, 300), (4101, 9, 333)):
+            t, y, yerr = synthetic_star(N, 40 + N)
+            tr = BatmanModel(cfg_tr)
+            tr.init_model(t, (t[1] - t[0]) if N > 1 else 0.0204, 6)
+            spec = build_spec(gp, tr)
+            np.random.seed(N)
+            W = 9
+            theta = np.hstack([gp.sample_prior(W), tr.sample_prior(W)])
+            ng = gp.ndim
+            theta[0, ng:ng + 5] = [0.31, 0.1, 0.1, 4.0, 88.0]      # several transits per tile
+            theta[1, ng:ng + 5] = [0.9, 0.2, 0.15, 1.6, 75.0]      # in transit (almost) everywhere
+            theta[2, ng:ng + 5] = [3.0, 1.0, 0.05, 10.0, 89.0]
+            theta[3, ng + 3] = np.nan                              # NaN semi-major axis
+            engine.clear_stars()
+            engine.set_model(spec)
+            y = y - 1e6            # no baseline: the transit depth is then a visible share of the residual
+            engine.upload_star(0, t, y, yerr)
+            engine.set_option("chunks", chunks)
+            engine.set_option("halo", halo)
+            lp, parts = engine.log_prob(theta, return_parts=True)
+            want_lp, want = oracle.log_prob(spec, t, y, yerr, theta, return_parts=True)
+            assert np.array_equal(np.isfinite(lp), np.isfinite(want_lp)), N
+            assert_parts_close(parts, want)
+    finally:
+        engine.set_option("chunks", 0)
+        engine.set_option("halo", 0)
