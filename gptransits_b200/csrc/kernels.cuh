@@ -1205,7 +1205,7 @@ __device__ __forceinline__ void fast_advance(const FastCoef<NT> &K, double ddt, 
 }
 
 #ifndef GP_UNROLL
-#define GP_UNROLL 2
+#define GP_UNROLL 4
 #endif
 #define GP_STR2(x) #x
 #define GP_STR(x) GP_STR2(x)
@@ -1219,6 +1219,9 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 	constexpr int J = 2 * NT;
 	constexpr int NP = J * (J + 1) / 2;
 	constexpr int CS = NP + J;  // carry size
+	// unroll factor of the step loop: 4 (measured best at J <= 6 once the loop was trimmed: profiles/r02_unroll_variants.log);
+	// 2 at J = 8, where four copies of the body spill
+	constexpr int GP_UNROLL_NT = NT >= 4 ? 2 : GP_UNROLL;
 
 	__shared__ __align__(128) double4 s_tile[NSTAGE][TILE];
 	__shared__ __align__(8) uint64_t s_bar[NSTAGE];
@@ -1448,7 +1451,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, GP_MINBLOCKS) gp_chunk_kernel(C
 			auto fast_range = [&](int a_, int b_, auto acc_tag, auto order_tag) {
 				constexpr bool ACC = decltype(acc_tag)::value;
 				constexpr int ORDER = decltype(order_tag)::value;
-GP_PRAGMA_UNROLL
+#pragma unroll GP_UNROLL_NT
 				for (int n = a_; n < b_; n++) {
 					const int m = min(n + 1, s1 - 1);
 					const double mv3 = load_mean(min(n + 3, s1 - 1));
