@@ -104,7 +104,8 @@ int gpt_model_set(gpt_engine *e, const gpt_model_desc *desc);
 /* Replaces celerite.GP.compute(t*0.0864, yerr=...) (model.py:183-187) plus the
  * light-curve members read by the likelihood (model.py:309-310: lc.time,
  * lc.flux).  t in days, y and yerr in the flux unit the caller fits in (the
- * reference: ppm).  yerr == NULL -> celerite's default 1.123e-12. */
+ * reference: ppm).  yerr == NULL -> celerite's default 1.123e-12.  A re-upload into the slot last uploaded with
+ * bit-identical time stamps (new fluxes or error bars on the same grid) keeps the analysis of the grid. */
 int gpt_star_upload(gpt_engine *e, int star, const double *t_days, const double *y,
 		    const double *yerr, int64_t N);
 /* The same for nstars stars observed on ONE time grid with one error array (a survey batch, slots star0 ..

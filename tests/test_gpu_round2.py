@@ -372,3 +372,38 @@ def test_transit_mask_on_edge_shapes(engine):
     finally:
         engine.set_option("chunks", 0)
         engine.set_option("halo", 0)
+
+
+def test_reupload_on_the_same_time_stamps_keeps_the_grid_analysis(engine):
+    """New fluxes / error bars on bit-identical time stamps in the slot last uploaded take the short path of
+    gpt_star_upload (counter "grid_reuse"); the result is the one a full upload gives, and any change of the time
+    stamps, of the length or of the presence of error bars takes the full path."""
+    np.random.seed(14)
+    gp = GPModel(C3_CONFIG_GP)
+    spec = build_spec(gp, None)
+    theta = gp.sample_prior(8)
+    t, y, yerr = synthetic_star(3000, 3)
+    y2, yerr2 = y + 40.0 * np.sin(t), yerr * 1.3
+    engine.clear_stars()
+    engine.set_model(spec)
+    engine.set_option("chunks", 1)
+    try:
+        engine.upload_star(0, t, y2, yerr2)
+        want = engine.log_prob(theta)
+        engine.clear_stars()
+        engine.upload_star(0, t, y, yerr)
+        n0 = engine.stat("grid_reuse")
+        engine.upload_star(0, t.copy(), y2, yerr2)          # same stamps, another buffer
+        assert engine.stat("grid_reuse") == n0 + 1
+        assert np.array_equal(engine.log_prob(theta), want)
+        t3 = t.copy()
+        t3[1234] += 1e-9
+        engine.upload_star(0, t3, y2, yerr2)                # a changed stamp
+        engine.upload_star(0, t3, y2, None)                 # no error bars
+        engine.upload_star(0, t3[:-1], y2[:-1], None)       # another length
+        assert engine.stat("grid_reuse") == n0 + 1
+        _, parts = engine.log_prob(theta, return_parts=True)
+        _, wparts = oracle.log_prob(spec, t3[:-1], y2[:-1], None, theta, return_parts=True)
+        assert_parts_close(parts, wparts)
+    finally:
+        engine.set_option("chunks", 0)
